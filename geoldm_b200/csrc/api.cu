@@ -1,0 +1,123 @@
+// C-ABI entry points: error plumbing, EGNN.forward orchestration, unit-level wrappers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace geoldm {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  float *h, *h2, *t1, *agg, *pq, *xa, *xb, *xagg;
+  size_t bytes;
+};
+static Workspace carve(void* base, int n_node, int H) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t n_floats) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align_up(n_floats * sizeof(float), 256);
+    return p;
+  };
+  const size_t nh = (size_t)n_node * H;
+  w.h = take(nh); w.h2 = take(nh); w.t1 = take(nh); w.agg = take(nh); w.pq = take(2 * nh);
+  w.xa = take((size_t)3 * n_node); w.xb = take((size_t)3 * n_node); w.xagg = take((size_t)3 * n_node);
+  w.bytes = off;
+  return w;
+}
+
+static int edge_dispatch(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
+                         const float* pq, const float* x, const float* x0, float* out, cudaStream_t st) {
+  if (cfg.mma_mode == GEOLDM_MMA_FP32_SIMT) return launch_edge_simt(cfg, w, b, equiv, pq, x, x0, out, st);
+  return launch_edge_tc(cfg, w, b, equiv, pq, x, x0, out, st);
+}
+}  // namespace geoldm
+
+using namespace geoldm;
+
+extern "C" {
+
+int geoldm_abi_version(void) { return GEOLDM_ABI_VERSION; }
+const char* geoldm_last_error(void) { return g_err; }
+
+size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node) {
+  return carve(nullptr, n_node, cfg->hidden_nf).bytes;
+}
+
+static int check_cfg(const geoldm_egnn_config* cfg) {
+  GEOLDM_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= GEOLDM_MAX_LAYERS, "n_layers %d not in [1,%d]", cfg->n_layers,
+                 GEOLDM_MAX_LAYERS);
+  GEOLDM_REQUIRE(cfg->inv_sublayers >= 1 && cfg->inv_sublayers <= GEOLDM_MAX_SUBLAYERS, "inv_sublayers %d not in [1,%d]",
+                 cfg->inv_sublayers, GEOLDM_MAX_SUBLAYERS);
+  GEOLDM_REQUIRE(cfg->hidden_nf % 32 == 0, "hidden_nf %d must be a multiple of 32", cfg->hidden_nf);
+  GEOLDM_REQUIRE(cfg->agg_div != 0.f, "agg_div must be non-zero");
+  GEOLDM_REQUIRE(cfg->mma_mode >= 0 && cfg->mma_mode <= 3, "bad mma_mode %d", cfg->mma_mode);
+  return 0;
+}
+
+int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights* w, const geoldm_batch* b,
+                        const float* h_in, const float* x_in, float* h_out, float* x_out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = b->n_node, H = cfg->hidden_nf;
+  if (N == 0) return 0;
+  Workspace ws = carve(workspace, N, H);
+  GEOLDM_REQUIRE(workspace && workspace_bytes >= ws.bytes, "egnn_forward: workspace %zu < %zu bytes", workspace_bytes,
+                 ws.bytes);
+  int rc;
+  if ((rc = launch_embed(N, H, cfg->in_node_nf, h_in, w->emb_w, w->emb_b, ws.h, st))) return rc;
+  const float* x_cur = x_in;  // EGNN-entry coordinates stay in x_in (d0 is recomputed from them)
+  float* x_bufs[2] = {ws.xa, ws.xb};
+  int xi = 0;
+  float *h = ws.h, *h2 = ws.h2;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    const geoldm_block& blk = w->block[l];
+    for (int s = 0; s < cfg->inv_sublayers; ++s) {
+      const geoldm_gcl& g = blk.gcl[s];
+      if ((rc = launch_linear(h, H, nullptr, 0, 1.f, g.edge.pq_wt, g.edge.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
+      cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
+      if ((rc = edge_dispatch(*cfg, g.edge, *b, false, ws.pq, x_cur, x_in, ws.agg, st))) return rc;
+      if ((rc = launch_linear(h, H, ws.agg, H, cfg->agg_div, g.node_w1t, g.node_b1, nullptr, 1, ws.t1, N, H, st))) return rc;
+      if ((rc = launch_linear(ws.t1, H, nullptr, 0, 1.f, g.node_w2t, g.node_b2, h, 2, h2, N, H, st))) return rc;
+      float* tmp = h; h = h2; h2 = tmp;
+    }
+    const geoldm_edge_mlp& e = blk.equiv;
+    if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
+    cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
+    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, x_cur, x_in, ws.xagg, st))) return rc;
+    float* x_next = (l + 1 == cfg->n_layers) ? x_out : x_bufs[xi];
+    if ((rc = launch_coord_update(3 * N, x_cur, ws.xagg, cfg->agg_div, x_next, st))) return rc;
+    x_cur = x_next;
+    xi ^= 1;
+  }
+  if ((rc = launch_outproj(N, H, cfg->out_node_nf, h, w->out_w, w->out_b, h_out, st))) return rc;
+  GEOLDM_CHECK_LAUNCH("egnn_forward");
+  return 0;
+}
+
+int geoldm_edge_gcl(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b, const float* pq,
+                    const float* x, const float* x0, float* agg, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  return edge_dispatch(*cfg, *w, *b, false, pq, x, x0, agg, (cudaStream_t)stream);
+}
+int geoldm_edge_equiv(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b, const float* pq,
+                      const float* x, const float* x0, float* xagg, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  return edge_dispatch(*cfg, *w, *b, true, pq, x, x0, xagg, (cudaStream_t)stream);
+}
+int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt, const float* bias,
+                  const float* res, int epi, float* out, int m, int n, int mma_mode, void* stream) {
+  (void)mma_mode;
+  return launch_linear(a1, k1, a2, k2, a2_div, wt, bias, res, epi, out, m, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

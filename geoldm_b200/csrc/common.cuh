@@ -1,0 +1,89 @@
+// Shared device helpers for the geoldm_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/geoldm_b200.h"
+
+namespace geoldm {
+
+// ---- error plumbing (thread-local text, integer codes) --------------------------------------
+void set_error(const char* fmt, ...);
+#define GEOLDM_CHECK_LAUNCH(what)                                                      \
+  do {                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) {                                                          \
+      geoldm::set_error("%s: %s", what, cudaGetErrorString(e__));                      \
+      return -2;                                                                       \
+    }                                                                                  \
+  } while (0)
+#define GEOLDM_REQUIRE(cond, ...)                                                      \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      geoldm::set_error(__VA_ARGS__);                                                  \
+      return -1;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+// ---- math -----------------------------------------------------------------------------------
+// SiLU(v) = v / (1 + exp(-v)).  ex2.approx + fast divide: ~2-3 ulp, unbiased; the reference's CPU
+// path uses a 1-ulp vectorised expf, so both sit at the fp32 noise floor.
+__device__ __forceinline__ float silu(float v) {
+  return __fdividef(v, 1.0f + __expf(-v));
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- cp.async (LDGSTS) 16-byte ----------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- per-edge geometry (coord2diff, egnn/egnn_new.py:249-255) ----------------------------------
+struct EdgeGeom {
+  float r;     // ||x_i - x_j||^2 at block entry
+  float d0;    // same on the coordinates at EGNN entry
+  float ux, uy, uz;  // (x_i - x_j) / (sqrt(r + 1e-8) + norm_constant)
+};
+__device__ __forceinline__ EdgeGeom edge_geom(const float* __restrict__ x, const float* __restrict__ x0, int i,
+                                              int j, float norm_constant) {
+  EdgeGeom g;
+  float dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+  // same association as torch.sum((d)**2, 1): ((dx^2 + dy^2) + dz^2), no FMA contraction
+  g.r = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  float ex = x0[3 * i] - x0[3 * j], ey = x0[3 * i + 1] - x0[3 * j + 1], ez = x0[3 * i + 2] - x0[3 * j + 2];
+  g.d0 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+  float den = __fadd_rn(__fsqrt_rn(__fadd_rn(g.r, 1e-8f)), norm_constant);
+  g.ux = __fdiv_rn(dx, den);
+  g.uy = __fdiv_rn(dy, den);
+  g.uz = __fdiv_rn(dz, den);
+  return g;
+}
+
+// ---- launchers implemented in the .cu files ----------------------------------------------------
+int launch_edge_simt(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
+                     const float* pq, const float* x, const float* x0, float* out, cudaStream_t st);
+int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
+                   const float* pq, const float* x, const float* x0, float* out, cudaStream_t st);
+int launch_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt,
+                  const float* bias, const float* res, int epi, float* out, int m, int n, cudaStream_t st);
+
+int launch_embed(int n_node, int H, int F, const float* h_in, const float* w, const float* b, float* h,
+                 cudaStream_t st);
+int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, const float* b, float* out,
+                   cudaStream_t st);
+int launch_coord_update(int n3, const float* x, const float* xagg, float div, float* x_next, cudaStream_t st);
+
+}  // namespace geoldm

@@ -1,0 +1,149 @@
+"""Ragged molecule packing: node_mask -> the geoldm_batch tables of include/geoldm_b200.h.
+
+Replaces the reference's padded layout + python edge-list builder (egnn/models.py:115-134
+get_adj_matrix; masks from qm9/sampling.py:118-128).  Real nodes of all molecules are stored
+back to back; edge rows are implicit (fully connected, i != j) and sorted by (molecule, receiver,
+sender) so that the segment sum over senders is a contiguous reduction.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TEMPLATES: Dict[int, tuple] = {}
+
+
+def _edge_template(n: int):
+    """(i, j) local indices of the n(n-1) ordered pairs, receiver-major."""
+    if n not in _TEMPLATES:
+        i = np.repeat(np.arange(n, dtype=np.int32), n)
+        j = np.tile(np.arange(n, dtype=np.int32), n)
+        keep = i != j
+        _TEMPLATES[n] = (i[keep], j[keep])
+    return _TEMPLATES[n]
+
+
+@dataclass
+class RaggedBatch:
+    n_nodes: np.ndarray                 # [B] atoms per molecule (host)
+    device: torch.device
+    mol_off: torch.Tensor               # int32 [B+1]
+    node_mol: torch.Tensor              # int32 [N]
+    edge_i: torch.Tensor                # int32 [E]
+    edge_j: torch.Tensor                # int32 [E]
+    node_src: Optional[torch.Tensor]    # int32 [N] row of the padded [B*n_max] layout, or None (already ragged)
+    mol_id: torch.Tensor                # int64 [B] global molecule ids (Philox keys)
+    n_max: int = 0                      # padded width of the layout node_src refers to
+    _tiles: Dict[int, tuple] = field(default_factory=dict)
+
+    @property
+    def n_mol(self) -> int:
+        return int(self.n_nodes.shape[0])
+
+    @property
+    def n_node(self) -> int:
+        return int(self.node_mol.shape[0])
+
+    @property
+    def n_edge(self) -> int:
+        return int(self.edge_i.shape[0])
+
+    def c_batch(self, tile_m: int) -> _lib.Batch:
+        """ctypes geoldm_batch for a given tile height (64: SIMT kernel, 128: tcgen05 kernel)."""
+        if tile_m not in self._tiles:
+            n_tile = (self.n_edge + tile_m - 1) // tile_m
+            rows = np.minimum(np.arange(n_tile + 1, dtype=np.int64) * tile_m, self.n_edge).astype(np.int32)
+            tile_row = torch.from_numpy(rows).to(self.device)
+            cb = _lib.Batch(self.n_mol, self.n_node, self.n_edge, n_tile, tile_m, _lib.ptr(self.mol_off).value,
+                            _lib.ptr(self.node_mol).value, _lib.ptr(self.edge_i).value, _lib.ptr(self.edge_j).value,
+                            _lib.ptr(tile_row).value)
+            self._tiles[tile_m] = (cb, tile_row)
+        return self._tiles[tile_m][0]
+
+    def edge_messages(self) -> int:
+        """Real ordered pairs (i != j) = sum n(n-1); SURVEY §8d's unit for EGNN edge-msgs."""
+        return self.n_edge
+
+
+def pack_molecules(n_nodes: Sequence[int], device, n_max: Optional[int] = None,
+                   positions: Optional[np.ndarray] = None, mol_ids: Optional[Sequence[int]] = None) -> RaggedBatch:
+    """Build the tables for molecules with `n_nodes[b]` atoms.
+
+    n_max given  -> node_src maps ragged node k to its row in a padded [B, n_max] layout
+                    (prefix masks unless `positions` — flat padded indices of the real nodes, sorted — is given).
+    n_max None   -> caller's tensors are already ragged (node_src None).
+    """
+    n_arr = np.asarray(n_nodes, dtype=np.int64).reshape(-1)
+    if (n_arr < 1).any():
+        raise ValueError("every molecule needs at least one atom")
+    if n_arr.max(initial=0) > 256:
+        raise ValueError("molecules with more than 256 atoms are not supported by the sampler kernels")
+    B = n_arr.shape[0]
+    off = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(n_arr, out=off[1:])
+    node_mol = np.repeat(np.arange(B, dtype=np.int32), n_arr)
+    ei, ej = [], []
+    for b in range(B):
+        ti, tj = _edge_template(int(n_arr[b]))
+        ei.append(ti + np.int32(off[b]))
+        ej.append(tj + np.int32(off[b]))
+    edge_i = np.concatenate(ei) if ei else np.zeros(0, np.int32)
+    edge_j = np.concatenate(ej) if ej else np.zeros(0, np.int32)
+    node_src = None
+    if n_max is not None:
+        if positions is None:
+            local = np.arange(off[-1], dtype=np.int64) - np.repeat(off[:-1], n_arr)
+            positions = node_mol.astype(np.int64) * n_max + local
+        node_src = torch.from_numpy(np.asarray(positions, dtype=np.int32)).to(device)
+    ids = np.arange(B, dtype=np.int64) if mol_ids is None else np.asarray(mol_ids, dtype=np.int64)
+    dev = torch.device(device)
+    return RaggedBatch(
+        n_nodes=n_arr, device=dev,
+        mol_off=torch.from_numpy(off.astype(np.int32)).to(dev), node_mol=torch.from_numpy(node_mol).to(dev),
+        edge_i=torch.from_numpy(edge_i.astype(np.int32)).to(dev), edge_j=torch.from_numpy(edge_j.astype(np.int32)).to(dev),
+        node_src=node_src, mol_id=torch.from_numpy(ids).to(dev), n_max=int(n_max or 0))
+
+
+def pack_from_masks(node_mask: torch.Tensor, edge_mask: Optional[torch.Tensor] = None,
+                    validate: bool = True) -> RaggedBatch:
+    """node_mask [bs, n, 1] (or [bs*n, 1] with bs inferred impossible -> must be 3-D) -> RaggedBatch.
+
+    The CUDA path assumes the reference's mask convention: edge_mask = outer(node_mask) minus the
+    diagonal (qm9/sampling.py:124-127, qm9/data/collate.py:88-97).  `validate` checks that once
+    (one device->host read per new mask)."""
+    if node_mask.dim() != 3:
+        raise ValueError("node_mask must be [bs, n_nodes, 1]")
+    bs, n, _ = node_mask.shape
+    nm = node_mask.detach().reshape(bs, n) != 0
+    nm_host = nm.cpu().numpy()
+    if validate and edge_mask is not None:
+        em = edge_mask.detach().reshape(bs, n, n) != 0
+        want = nm.unsqueeze(1) & nm.unsqueeze(2) & ~torch.eye(n, dtype=torch.bool, device=nm.device).unsqueeze(0)
+        if not bool(torch.equal(em, want)):
+            raise ValueError("edge_mask is not outer(node_mask) minus the diagonal; the ragged kernels "
+                             "only implement the reference's fully connected convention")
+    n_arr = nm_host.sum(1)
+    if (n_arr == 0).any():
+        raise ValueError("node_mask has an empty molecule")
+    positions = np.flatnonzero(nm_host.reshape(-1))
+    return pack_molecules(n_arr, node_mask.device, n_max=n, positions=positions)
+
+
+def balance_shards(n_nodes: Sequence[int], world_size: int):
+    """Greedy longest-processing-time split of molecules over ranks by edge count n(n-1).
+    Returns a list (per rank) of index arrays into n_nodes, each sorted ascending."""
+    n_arr = np.asarray(n_nodes, dtype=np.int64)
+    cost = n_arr * (n_arr - 1) + n_arr  # edges + a node term so that n=1 molecules still count
+    order = np.argsort(-cost, kind="stable")
+    loads = np.zeros(world_size, dtype=np.int64)
+    shards = [[] for _ in range(world_size)]
+    for idx in order:
+        r = int(np.argmin(loads))
+        shards[r].append(int(idx))
+        loads[r] += cost[idx]
+    return [np.array(sorted(s), dtype=np.int64) for s in shards]

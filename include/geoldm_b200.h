@@ -1,0 +1,172 @@
+/*
+ * geoldm_b200.h — C ABI of the B200-native GeoLDM EGNN-denoiser sampling path.
+ *
+ * The reference (mint258/GeoLDM) is pure Python/PyTorch and has NO plugin/FFI layer for this path
+ * (SURVEY.md §8b): the boundary there is the Python call
+ *     EnVariationalDiffusion.phi -> self.dynamics._forward(t, xh, node_mask, edge_mask, context)
+ *                                                   (equivariant_diffusion/en_diffusion.py:314-317)
+ * and, one level up, generative_model.sample(...)   (qm9/sampling.py:139).
+ * This header is therefore the interface a maintainer binds (ctypes stub in INTEGRATION.md) to
+ * replace the bodies of the functions cited on each entry point below.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - all floating point is fp32, indices int32, row-major, ragged-packed (no padding): real
+ *     nodes of all molecules are concatenated, N = sum n_b; edges are implicit (fully connected
+ *     within a molecule, i != j) and described by the geoldm_batch tables;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*), performs no
+ *     allocation and no host synchronisation (CUDA-graph capturable); workspace is caller-owned;
+ *   - return value 0 = ok, <0 = error; geoldm_last_error() returns the text (thread-local).
+ */
+#ifndef GEOLDM_B200_H
+#define GEOLDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEOLDM_MAX_LAYERS 16
+#define GEOLDM_MAX_SUBLAYERS 4
+#define GEOLDM_ABI_VERSION 1
+
+/* arithmetic mode of the 256x256 edge/node contractions */
+enum {
+  GEOLDM_MMA_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores (exact fp32 products)               */
+  GEOLDM_MMA_3XTF32 = 1,      /* tcgen05 kind::tf32, hi*hi + hi*lo + lo*hi, fp32 accumulate  */
+  GEOLDM_MMA_TF32 = 2,        /* tcgen05 kind::tf32 single pass (fast mode, fails 1e-5 gate) */
+  GEOLDM_MMA_BF16 = 3         /* tcgen05 kind::f16 bf16 single pass (fast mode)              */
+};
+
+/* Mirrors the ctor kwargs of EGNN / EGNN_dynamics_QM9 (egnn/egnn_new.py:151-153, egnn/models.py:9-13). */
+typedef struct {
+  int hidden_nf;             /* nf; one of 32, 64, 128, 192, 256                            */
+  int n_layers;              /* number of EquivariantBlocks                                 */
+  int inv_sublayers;         /* GCLs per block                                              */
+  int in_node_nf;            /* features entering `embedding` (latent + time + context)     */
+  int out_node_nf;           /* features leaving `embedding_out`                            */
+  int attention;             /* GCL attention gate                                          */
+  int tanh;                  /* tanh-bounded coordinate message                             */
+  float norm_constant;       /* coord2diff denominator constant                             */
+  float coords_range;        /* 15.0 per block (not /n_layers; egnn_new.py:160 vs :178)     */
+  float agg_div;             /* 'sum': normalization_factor; 'mean': padded n_max           */
+  int mma_mode;              /* GEOLDM_MMA_*                                                */
+} geoldm_egnn_config;
+
+/* One edge MLP (GCL.edge_mlp+att_mlp, egnn_new.py:14-28; or EquivariantUpdate.coord_mlp, :75-82),
+ * with the first layer split per node:  W1 [H,2H+2] -> pq_wt = [W1[:, :H]^T | W1[:, H:2H]^T]. */
+typedef struct {
+  const float* pq_wt;        /* [H][2H]  (k-major: row k holds the 2H outputs)              */
+  const float* pq_b;         /* [2H]     first-layer bias in [0,H), zeros in [H,2H)         */
+  const float* w_rd;         /* [2][H]   W1[:, 2H] (current d^2), W1[:, 2H+1] (entry d^2)   */
+  const float* w2t;          /* [H][H]   second layer, transposed (k-major)                 */
+  const float* b2;           /* [H]                                                         */
+  const float* w_out;        /* [H]      att_mlp.0.weight  |  coord_mlp.4.weight            */
+  const float* b_out;        /* [1]      att_mlp.0.bias    |  NULL                          */
+  const void* tc_pack;       /* mode-specific tensor-core operand pack of w2 (or NULL)      */
+} geoldm_edge_mlp;
+
+typedef struct {
+  geoldm_edge_mlp edge;
+  const float* node_w1t;     /* [2H][H]  node_mlp.0 transposed: rows [0,H) act on h, [H,2H) on agg */
+  const float* node_b1;      /* [H]                                                         */
+  const float* node_w2t;     /* [H][H]   node_mlp.2 transposed                              */
+  const float* node_b2;      /* [H]                                                         */
+} geoldm_gcl;
+
+typedef struct {
+  geoldm_gcl gcl[GEOLDM_MAX_SUBLAYERS];
+  geoldm_edge_mlp equiv;
+} geoldm_block;
+
+typedef struct {
+  const float* emb_w;        /* [H][in_node_nf]  (PyTorch layout)                           */
+  const float* emb_b;        /* [H]                                                         */
+  const float* out_w;        /* [out_node_nf][H]                                            */
+  const float* out_b;        /* [out_node_nf]                                               */
+  geoldm_block block[GEOLDM_MAX_LAYERS];
+} geoldm_egnn_weights;
+
+/* Ragged batch tables (replace get_adj_matrix + node_mask/edge_mask, egnn/models.py:115-134,
+ * qm9/sampling.py:118-128).  Edge rows are sorted by (molecule, receiver i, sender j != i). */
+typedef struct {
+  int n_mol, n_node, n_edge, n_tile, tile_m;
+  const int* mol_off;        /* [n_mol+1] first node of each molecule                       */
+  const int* node_mol;       /* [n_node]  molecule of each node                             */
+  const int* edge_i;         /* [n_edge]  receiver (aggregation index, `row`)               */
+  const int* edge_j;         /* [n_edge]  sender (`col`)                                    */
+  const int* tile_row;       /* [n_tile+1] first edge row of each tile; rows per tile <= tile_m */
+} geoldm_batch;
+
+int geoldm_abi_version(void);
+const char* geoldm_last_error(void);
+/* 1 if the library was built with the tcgen05 kernels for sm_100a */
+int geoldm_has_tcgen05(void);
+
+/* ---- whole-network entry point: EGNN.forward (egnn/egnn_new.py:184-197) ------------------- */
+size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node);
+int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights* w, const geoldm_batch* b,
+                        const float* h_in,  /* [N][in_node_nf] */
+                        const float* x_in,  /* [N][3] */
+                        float* h_out,       /* [N][out_node_nf] */
+                        float* x_out,       /* [N][3] final coordinates */
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- EGNN_dynamics_QM9._forward glue (egnn/models.py:56-76 and :80-113) ------------------- */
+/* Gathers real nodes from the caller's (possibly padded) xh, appends time/context features.
+ * node_src[k] = flat row of xh holding ragged node k.  t_mol: per-molecule time [n_mol] or NULL;
+ * if NULL the time is t_table[*step_idx_dev] (sampler) .  context: [rows][ctx_nf] or NULL. */
+int geoldm_dynamics_prep(const geoldm_batch* b, const int* node_src, const float* xh, int xh_dim,
+                         const float* t_mol, const float* t_table, const int* step_idx_dev,
+                         const float* context, int ctx_nf, int condition_time,
+                         float* h_in, int in_node_nf, float* x, void* stream);
+/* vel = x_final - x_in (delta!=0) or x_final; drops time/context columns; NaN guard over the whole
+ * batch (models.py:100-102); remove_mean_with_mask (utils.py:31-38); writes out[node_src[k]].
+ * nan_flag: device int, must be zero on entry of geoldm_dynamics_finish_a. */
+int geoldm_dynamics_finish_a(const geoldm_batch* b, const float* x_in, const float* x_final, int delta,
+                             float* vel, int* nan_flag, void* stream);
+int geoldm_dynamics_finish_b(const geoldm_batch* b, const int* node_src, const float* vel, const float* h_out,
+                             int h_stride, int h_keep, const int* nan_flag, float* out, int out_dim,
+                             void* stream);
+
+/* ---- sampler (equivariant_diffusion/en_diffusion.py:716-795, 1099-1122) -------------------- */
+/* z_s = z_t/alpha_ts - c_eps*eps_hat + sigma*noise, then CoM projection of the x part.
+ * coef: [n_steps][4] = {alpha_ts, c_eps, sigma, t}; row *step_idx_dev is used.  noise is either
+ * caller-provided (injected, ragged layout of z; draw d lives at noise + d*noise_stride floats, d =
+ * *draw_idx_dev) or NULL -> Philox4x32-10 keyed by (seed, mol_id[m]),
+ * counter (draw index *draw_idx_dev, node, column); noise x-part is mean-centred per molecule.
+ * mode 0: p(z_s|z_t) update;  mode 1: p(x|z_0): out = (z - sigma0*eps)/alpha0 + sigma_x*noise with
+ * coef row = {alpha0, sigma0, sigma_x, 0};  mode 2: out = noise (initial z_T). */
+int geoldm_sampler_update(const geoldm_batch* b, int mode, const float* coef, const int* step_idx_dev,
+                          const float* z, const float* eps_hat, const float* noise, size_t noise_stride, int dim,
+                          uint64_t seed, const int64_t* mol_id, const int* draw_idx_dev,
+                          float* z_out, void* stream);
+/* *step_idx_dev += d_step; *draw_idx_dev += d_draw (single thread; keeps the loop graph-replayable) */
+int geoldm_sampler_advance(int* step_idx_dev, int d_step, int* draw_idx_dev, int d_draw, void* stream);
+
+/* ---- unit-level entry points (used by tests; same kernels as the forward) ------------------ */
+/* a1+a3 edge part: agg[i] += sum_j e_ij (raw sum; caller zeroes agg and divides by agg_div) */
+int geoldm_edge_gcl(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b,
+                    const float* pq, const float* x, const float* x0, float* agg, void* stream);
+/* a1+a4: xagg[i] += sum_j u_ij * tanh(s_ij) * coords_range (raw sum) */
+int geoldm_edge_equiv(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b,
+                      const float* pq, const float* x, const float* x0, float* xagg, void* stream);
+/* out[M][N] = epi(a1[M][k1] * wt[0:k1] + (a2[M][k2]/a2_div) * wt[k1:k1+k2] + bias); epi: 0 none, 1 SiLU,
+ * 2 residual (out = res + ...).  wt is k-major [k1+k2][N]. */
+int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt,
+                  const float* bias, const float* res, int epi, float* out, int m, int n, int mma_mode,
+                  void* stream);
+/* Philox4x32-10 standard normals (Box-Muller), the sampler's noise stream exposed for tests:
+ * out[4*d+e] = e-th normal of block counter=(d, node, blk, seed>>32), key=(mol_id, (uint32)seed), i.e. what
+ * geoldm_sampler_update draws for draw index d, node `node` of molecule `mol_id`, columns 4*blk+e. */
+int geoldm_philox_normal(uint64_t seed, uint64_t mol_id, uint32_t node, uint32_t blk, float* out, int n,
+                         void* stream);
+/* EnHierarchicalVAE.decode tail (en_diffusion.py:1028-1033): one_hot = onehot(argmax(h[:, :n_cat]), n_classes),
+ * charges = round(h[:, charge_col]) (charge_col < 0: none).  Outputs int64, ragged [N][n_classes] / [N]. */
+int geoldm_decode(int n_node, const float* h, int h_dim, int n_cat, int n_classes, int charge_col,
+                  long long* one_hot, long long* charges, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOLDM_B200_H */

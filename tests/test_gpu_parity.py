@@ -1,0 +1,345 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's golden vectors and the CPU oracle.
+
+Metric everywhere: err = max|a-b| / max|b| per part (x columns, h columns).
+Gate (north_star): fp32 single forward <= 1e-5.  Noise floor of the reference itself (fp32 vs fp64): 4.6e-6.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geoldm_oracle as O
+from tests.helpers import build_cuda_model, load_golden, part_errors
+
+pytestmark = pytest.mark.gpu
+FWD_TOL = 1e-5
+MODES = ["fp32"]
+
+
+def _has_tc():
+    from geoldm_b200 import _lib
+    return bool(_lib.lib().geoldm_has_tcgen05())
+
+
+def modes():
+    return MODES + (["3xtf32"] if _has_tc() else [])
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def cuda_masks(nodes, n_max, dev):
+    nm, em = O.build_masks(nodes, n_max)
+    return nm.to(dev), em.to(dev)
+
+
+# ---------------------------------------------------------------------------------------------------
+# unit level
+# ---------------------------------------------------------------------------------------------------
+def test_library_is_the_cuda_build(dev):
+    from geoldm_b200 import _lib
+    assert _lib.lib().geoldm_abi_version() == 1
+
+
+@pytest.mark.parametrize("m,k1,k2,n,epi", [(1154, 256, 0, 512, 0), (1154, 256, 256, 256, 1), (333, 192, 0, 192, 2),
+                                            (64, 32, 32, 32, 1), (5, 64, 0, 128, 0)])
+def test_linear_kernel(dev, m, k1, k2, n, epi):
+    from geoldm_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    a1 = torch.randn(m, k1, generator=g)
+    a2 = torch.randn(m, k2, generator=g) if k2 else None
+    wt = torch.randn(k1 + k2, n, generator=g) / np.sqrt(k1 + k2)
+    bias = torch.randn(n, generator=g)
+    res = torch.randn(m, n, generator=g)
+    div = 3.0 if k2 else 1.0
+    a = a1 if a2 is None else torch.cat([a1, a2 / div], 1)
+    ref = a.double() @ wt.double() + bias.double()
+    if epi == 1:
+        ref = torch.nn.functional.silu(ref)
+    if epi == 2:
+        ref = ref + res.double()
+    out = torch.empty(m, n, device=dev)
+    d = lambda t: None if t is None else t.to(dev)
+    A1, A2, WT, B, R = d(a1), d(a2), d(wt), d(bias), d(res)
+    _lib.check(_lib.lib().geoldm_linear(_lib.ptr(A1), k1, _lib.ptr(A2), k2, div, _lib.ptr(WT), _lib.ptr(B), _lib.ptr(R),
+                                        epi, _lib.ptr(out), m, n, 0, None), "linear")
+    torch.cuda.synchronize()
+    assert O.err_metric(out.cpu().double(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("H,nodes", [(256, [29, 3, 17, 18, 5]), (64, [9, 2, 1, 30]), (192, [12, 25]), (32, [70, 4])])
+@pytest.mark.parametrize("mode", ["fp32", "3xtf32"])
+def test_edge_kernels_vs_oracle(dev, H, nodes, mode):
+    """geoldm_edge_gcl / geoldm_edge_equiv vs the oracle's edge_model + unsorted_segment_sum."""
+    if mode != "fp32" and not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    from geoldm_b200 import _lib
+    from geoldm_b200.egnn import EGNN, TILE_M
+    from geoldm_b200.packing import pack_molecules
+    torch.manual_seed(1)
+    cfg = O.OracleConfig(nf=H, n_layers=1)
+    sd = O.make_state_dict(cfg, 5)
+    egnn = EGNN(in_node_nf=cfg.dyn_in_nf, in_edge_nf=1, hidden_nf=H, device=dev, n_layers=1, attention=True, tanh=True,
+                norm_constant=1, inv_sublayers=1, normalization_factor=1, aggregation_method='sum', mma_mode=mode)
+    egnn.load_state_dict({k[len("dynamics.egnn."):]: v for k, v in sd.items() if k.startswith("dynamics.egnn.")})
+    w, _keep = egnn.packed()
+    batch = pack_molecules(nodes, dev)
+    N = batch.n_node
+    h = torch.randn(N, H)
+    x = torch.randn(N, 3) * 2
+    x0 = torch.randn(N, 3) * 2
+    # oracle on the ragged edge list
+    row, col = batch.edge_i.cpu().long(), batch.edge_j.cpu().long()
+    r, u = O.coord2diff(x, row, col, 1.0)
+    d0, _ = O.coord2diff(x0, row, col, 1.0)
+    ea = torch.cat([r, d0], 1)
+    p = "dynamics.egnn.e_block_0."
+    e_in = torch.cat([h[row], h[col], ea], 1)
+    F = torch.nn.functional
+    m = F.silu(F.linear(F.silu(F.linear(e_in, sd[p + "gcl_0.edge_mlp.0.weight"], sd[p + "gcl_0.edge_mlp.0.bias"])),
+                        sd[p + "gcl_0.edge_mlp.2.weight"], sd[p + "gcl_0.edge_mlp.2.bias"]))
+    m = m * torch.sigmoid(F.linear(m, sd[p + "gcl_0.att_mlp.0.weight"], sd[p + "gcl_0.att_mlp.0.bias"]))
+    agg_ref = O.segment_sum(m, row, N, 1.0, "sum")
+    s = F.linear(F.silu(F.linear(F.silu(F.linear(e_in, sd[p + "gcl_equiv.coord_mlp.0.weight"],
+                                                 sd[p + "gcl_equiv.coord_mlp.0.bias"])),
+                                 sd[p + "gcl_equiv.coord_mlp.2.weight"], sd[p + "gcl_equiv.coord_mlp.2.bias"])),
+                 sd[p + "gcl_equiv.coord_mlp.4.weight"])
+    xagg_ref = O.segment_sum(u * torch.tanh(s) * 15.0, row, N, 1.0, "sum")
+    # CUDA: projections through geoldm_linear, then the fused edge kernels
+    L = _lib.lib()
+    cfgc = egnn.c_config()
+    cb = batch.c_batch(TILE_M[cfgc.mma_mode])
+    hd, xd, x0d = h.to(dev), x.to(dev), x0.to(dev)
+    pq = torch.empty(N, 2 * H, device=dev)
+    for which, ref in (("gcl", agg_ref), ("equiv", xagg_ref)):
+        em = w.block[0].gcl[0].edge if which == "gcl" else w.block[0].equiv
+        _lib.check(L.geoldm_linear(_lib.ptr(hd), H, None, 0, 1.0, em.pq_wt, em.pq_b, None, 0, _lib.ptr(pq), N, 2 * H,
+                                   cfgc.mma_mode, None), "linear")
+        out = torch.zeros(N, H if which == "gcl" else 3, device=dev)
+        fn = L.geoldm_edge_gcl if which == "gcl" else L.geoldm_edge_equiv
+        _lib.check(fn(C.byref(cfgc), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xd), _lib.ptr(x0d), _lib.ptr(out),
+                      None), which)
+        torch.cuda.synchronize()
+        err = O.err_metric(out.cpu(), ref)
+        assert err < 3e-6, (which, err)
+
+
+# ---------------------------------------------------------------------------------------------------
+# network level, against the reference's golden outputs
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("tag", ["s1", "s30"])
+def test_qm9_forward_golden(dev, tag, mode):
+    if mode != "fp32" and not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    cfg, sd, a, _ = load_golden("qm9_forward")
+    model = build_cuda_model(cfg, sd, dev, mode)
+    nm, em = cuda_masks(a["nodes"].tolist(), 29, dev)
+    z = a[f"z_{tag}"].to(dev)
+    for key, t in (("out_tscalar", torch.tensor([[0.5]])), ("out_tvec", a[f"t_vec_{tag}"]),
+                   ("out_t0", torch.zeros(z.shape[0], 1))):
+        out = model.dynamics._forward(t.to(dev), z, nm, em, None).cpu()
+        ex, eh = part_errors(out, a[f"{key}_{tag}"])
+        print(f"[parity] qm9_forward {tag} {key} mode={mode}: x {ex:.2e} h {eh:.2e}")
+        assert ex < FWD_TOL and eh < FWD_TOL, (key, ex, eh)
+        assert float((out * (1 - nm.cpu())).abs().max()) == 0.0
+        assert float(out[..., :3].sum(1).abs().max()) < 1e-4     # CoM-free
+
+
+@pytest.mark.parametrize("mode", ["fp32", "3xtf32"])
+def test_qm9_decoder_and_decode_golden(dev, mode):
+    if mode != "fp32" and not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    cfg, sd, a, _ = load_golden("qm9_forward")
+    model = build_cuda_model(cfg, sd, dev, mode)
+    nm, em = cuda_masks(a["nodes"].tolist(), 29, dev)
+    dx, dh = model.vae.decoder._forward(a["dec_in"].to(dev), nm, em, None)
+    assert O.err_metric(dx.cpu(), a["dec_x"]) < FWD_TOL and O.err_metric(dh.cpu(), a["dec_h"]) < FWD_TOL
+    x, h = model.vae.decode(a["dec_in"].to(dev), nm, em, None)
+    assert O.err_metric(x.cpu(), a["decode_x"]) < FWD_TOL
+    assert torch.equal(h["categorical"].cpu().long(), a["decode_onehot"].long())
+    assert torch.equal(h["integer"].cpu().long(), a["decode_charges"].long())
+
+
+@pytest.mark.parametrize("name", ["small_default", "small_S2_noatt_notanh", "small_mean", "small_cond", "small_latent2"])
+def test_small_variants_golden(dev, name):
+    cfg, sd, a, _ = load_golden(name)
+    model = build_cuda_model(cfg, sd, dev)
+    nm, em = cuda_masks(a["nodes"].tolist(), 29, dev)
+    ctx = a["context"].to(dev) if "context" in a else None
+    out = model.dynamics._forward(a["t_vec"].to(dev), a["z"].to(dev), nm, em, ctx).cpu()
+    ex, eh = part_errors(out, a["out"])
+    assert ex < FWD_TOL and eh < FWD_TOL, (ex, eh)
+    dx, dh = model.vae.decoder._forward(a["z"].to(dev), nm, em, ctx)
+    assert O.err_metric(dx.cpu(), a["dec_x"]) < FWD_TOL and O.err_metric(dh.cpu(), a["dec_h"]) < FWD_TOL
+
+
+@pytest.mark.parametrize("mode", ["fp32", "3xtf32"])
+def test_geom_forward_golden(dev, mode):
+    if mode != "fp32" and not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    cfg, sd, a, _ = load_golden("geom_forward")
+    model = build_cuda_model(cfg, sd, dev, mode)
+    nm, em = cuda_masks(a["nodes"].tolist(), 181, dev)
+    out = model.dynamics._forward(torch.tensor([[0.3]], device=dev), a["z"].to(dev), nm, em, None).cpu()
+    ex, eh = part_errors(out, a["out"])
+    print(f"[parity] geom_forward mode={mode}: x {ex:.2e} h {eh:.2e}")
+    assert ex < FWD_TOL and eh < FWD_TOL, (ex, eh)
+
+
+# ---------------------------------------------------------------------------------------------------
+# sampler
+# ---------------------------------------------------------------------------------------------------
+def test_sampler_steps_teacher_forced_golden(dev):
+    """P4: feed the reference's own z_t, compare eps_hat and z_s of every stored step; then P5 free-run."""
+    cfg, sd, a, _ = load_golden("qm9_sampler_steps")
+    model = build_cuda_model(cfg, sd, dev)
+    nodes = a["nodes"].tolist()
+    bs, T = len(nodes), cfg.diffusion_steps
+    nm, em = cuda_masks(nodes, 29, dev)
+    raw = a["raw"].float()
+    for k, s in enumerate(reversed(range(T - 4, T))):
+        s_arr = torch.full((bs, 1), float(s), device=dev) / T
+        t_arr = torch.full((bs, 1), float(s + 1), device=dev) / T
+        zt = a["z"][k].to(dev)
+        eps = model.phi(zt, t_arr, nm, em, None).cpu()
+        ex, eh = part_errors(eps, a["eps"][k])
+        assert ex < FWD_TOL and eh < FWD_TOL, ("eps", k, ex, eh)
+        zs = model.sample_p_zs_given_zt(s_arr, t_arr, zt, nm, em, None, noise=raw[k + 1]).cpu()
+        ex, eh = part_errors(zs, a["z"][k + 1])
+        assert ex < FWD_TOL and eh < FWD_TOL, ("zs", k, ex, eh)
+
+
+def test_sampler_free_run_first_steps_golden(dev):
+    """P5 (short): fused ragged sampler with injected noise reproduces the reference's first 4 steps."""
+    from geoldm_b200.packing import pack_molecules
+    cfg, sd, a, _ = load_golden("qm9_sampler_steps")
+    model = build_cuda_model(cfg, sd, dev)
+    nodes = a["nodes"].tolist()
+    batch = pack_molecules(nodes, dev, n_max=29)
+    src = batch.node_src.long().cpu()
+    T, D = cfg.diffusion_steps, 3 + cfg.latent_nf
+    raw = a["raw"].float().reshape(a["raw"].shape[0], -1, D)[:, src]
+    noise = torch.zeros(T + 2, batch.n_node, D)
+    noise[:raw.shape[0]] = raw
+    for graph in (False, True):
+        model.use_cuda_graph = graph
+        z4 = model.sample_latent_ragged(batch, noise=noise.to(dev), n_steps=4).cpu()
+        ref = a["z"][4].reshape(-1, D)[src]
+        ex, eh = part_errors(z4, ref)
+        print(f"[parity] free-run 4 steps graph={graph}: x {ex:.2e} h {eh:.2e}")
+        assert ex < 1e-5 and eh < 1e-5, (graph, ex, eh)
+
+
+def test_full_sample_small_tamed_T1000_golden(dev):
+    """Complete sample() (1000 steps + z0 -> x + decoder) vs the reference run of qm9/sampling.py:sample with
+    torch.manual_seed(77): the noise is regenerated in the reference's draw order and injected.
+    Gate (north_star): final coordinates within 1e-3; decoded atom types / charges identical."""
+    from geoldm_b200.sampling import sample
+    cfg, sd, a, _ = load_golden("small_tamed_sample_T1000")
+    model = build_cuda_model(cfg, sd, dev)
+    nodes = a["nodes"]
+    bs, n, T = len(nodes), 29, cfg.diffusion_steps
+    torch.manual_seed(int(a["torch_seed"][0]))
+    draws = []
+    for _ in range(T + 2):
+        zx = torch.randn(bs, n, 3)
+        zh = torch.randn(bs, n, cfg.latent_nf)
+        draws.append(torch.cat([zx, zh], 2))
+    noise = torch.stack(draws)
+    from tests.helpers import make_args
+    args = make_args(cfg)
+    info = {"max_n_nodes": 29}
+    one_hot, charges, x, node_mask = sample(args, dev, model, info, nodesxsample=nodes, noise=noise)
+    err = O.err_metric(x.cpu(), a["x"])
+    print(f"[parity] 1000-step tamed trajectory: final x err {err:.2e}")
+    assert err < 1e-3
+    assert torch.equal(one_hot.cpu().long(), a["one_hot"].long())
+    assert torch.equal(charges.cpu().long(), a["charges"].long())
+
+
+# ---------------------------------------------------------------------------------------------------
+# properties at BASELINE sizes (config 1/2: QM9, bs=64)
+# ---------------------------------------------------------------------------------------------------
+def _config1(dev, mode="fp32", bs=64, seed=0):
+    from geoldm_b200.histograms import QM9_WITH_H_N_NODES
+    cfg = O.QM9_CFG
+    sd = O.make_state_dict(cfg, 0)
+    model = build_cuda_model(cfg, sd, dev, mode)
+    torch.manual_seed(seed)
+    nodes = O.nodes_distribution_sample(QM9_WITH_H_N_NODES, bs).tolist()
+    nm, em = O.build_masks(nodes, 29)
+    z = torch.randn(bs, 29, 4) * nm
+    z = torch.cat([O.remove_mean_with_mask(z[..., :3], nm), z[..., 3:]], 2)
+    return cfg, sd, model, nodes, nm, em, z
+
+
+def test_config1_forward_vs_oracle_and_equivariance(dev):
+    cfg, sd, model, nodes, nm, em, z = _config1(dev)
+    t = torch.randint(0, 1001, (len(nodes), 1)).float() / 1000
+    ref = O.dynamics_forward(sd, cfg, t, z, nm, em)
+    out = model.dynamics._forward(t.to(dev), z.to(dev), nm.to(dev), em.to(dev), None).cpu()
+    ex, eh = part_errors(out, ref)
+    print(f"[parity] config1 bs=64 forward vs oracle: x {ex:.2e} h {eh:.2e}")
+    assert ex < FWD_TOL and eh < FWD_TOL
+    # run-to-run determinism
+    out2 = model.dynamics._forward(t.to(dev), z.to(dev), nm.to(dev), em.to(dev), None).cpu()
+    assert torch.equal(out, out2)
+    # E(3): random proper rotation (translation is a no-op in the CoM-free subspace)
+    q, _ = torch.linalg.qr(torch.randn(3, 3))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    zr = torch.cat([z[..., :3] @ q.T, z[..., 3:]], 2)
+    outr = model.dynamics._forward(t.to(dev), zr.to(dev), nm.to(dev), em.to(dev), None).cpu()
+    e_x = O.err_metric(outr[..., :3], out[..., :3] @ q.T)
+    e_h = O.err_metric(outr[..., 3:], out[..., 3:])
+    print(f"[equivariance] rotation: x {e_x:.2e}, h invariance {e_h:.2e} (reference itself: 4.2e-6 / 3.0e-7)")
+    assert e_x < 2e-5 and e_h < 5e-6
+
+
+def test_ragged_equals_padded_in_batch(dev):
+    """A molecule evaluated alone equals the same molecule inside a batch."""
+    cfg, sd, model, nodes, nm, em, z = _config1(dev, bs=16)
+    t = torch.tensor([[0.4]])
+    full = model.dynamics._forward(t.to(dev), z.to(dev), nm.to(dev), em.to(dev), None).cpu()
+    for b in (0, 7, 15):
+        nmb, emb = O.build_masks([nodes[b]], 29)
+        one = model.dynamics._forward(t.to(dev), z[b:b + 1].to(dev), nmb.to(dev), emb.to(dev), None).cpu()
+        assert O.err_metric(one[0], full[b]) < 2e-6
+
+
+def test_philox_noise_stream(dev):
+    """Device Philox4x32-10 + Box-Muller vs a numpy restatement (tests/philox_ref.py)."""
+    from geoldm_b200 import _lib
+    from tests.philox_ref import philox_normal4
+    out = torch.empty(64, device=dev)
+    seed, mol, node, blk = 0x1234567890ABCDEF, 42, 7, 1
+    _lib.check(_lib.lib().geoldm_philox_normal(seed, mol, node, blk, _lib.ptr(out), 64, None), "philox")
+    got = out.cpu().numpy()
+    for d in range(16):
+        want = philox_normal4(d, node, blk, seed >> 32, mol, seed & 0xFFFFFFFF)
+        assert np.allclose(got[4 * d:4 * d + 4], want, rtol=2e-5, atol=2e-6), (d, got[4 * d:4 * d + 4], want)
+
+
+def test_philox_sampler_statistics_and_shard_invariance(dev):
+    """z_T from the device RNG: CoM-free, unit variance, and keyed by global molecule id."""
+    from geoldm_b200.packing import pack_molecules
+    cfg, sd, model, nodes, nm, em, z = _config1(dev, bs=64)
+    ids = np.arange(64) + 1000
+    b_all = pack_molecules(nodes, dev, mol_ids=ids)
+    za = model.sample_latent_ragged(b_all, seed=3, n_steps=0).cpu()
+    off = b_all.mol_off.cpu().numpy()
+    for m in range(64):
+        blk = za[off[m]:off[m + 1]]
+        assert float(blk[:, :3].sum(0).abs().max()) < 1e-4
+    assert abs(float(za[:, 3:].std()) - 1.0) < 0.1
+    sel = [5, 9, 33]
+    b_sub = pack_molecules([nodes[i] for i in sel], dev, mol_ids=ids[sel])
+    zs = model.sample_latent_ragged(b_sub, seed=3, n_steps=0).cpu()
+    o2 = b_sub.mol_off.cpu().numpy()
+    for k, i in enumerate(sel):
+        assert torch.equal(zs[o2[k]:o2[k + 1]], za[off[i]:off[i + 1]])
