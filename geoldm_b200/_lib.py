@@ -51,10 +51,10 @@ _SIGS = {
     "geoldm_has_tcgen05": (C.c_int, []),
     "geoldm_egnn_workspace_bytes": (C.c_size_t, [C.POINTER(EgnnConfig), C.c_int]),
     "geoldm_egnn_forward": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EgnnWeights), C.POINTER(Batch), fp, fp, fp, fp,
-                                      fp, C.c_size_t, fp]),
+                                      fp, fp, C.c_size_t, fp]),
     "geoldm_dynamics_prep": (C.c_int, [C.POINTER(Batch), fp, fp, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp,
                                        C.c_int, fp, fp]),
-    "geoldm_dynamics_finish_a": (C.c_int, [C.POINTER(Batch), fp, fp, C.c_int, fp, fp, fp]),
+    "geoldm_dynamics_finish_a": (C.c_int, [C.POINTER(Batch), fp, fp, fp]),
     "geoldm_dynamics_finish_b": (C.c_int, [C.POINTER(Batch), fp, fp, fp, C.c_int, C.c_int, fp, fp, C.c_int, fp]),
     "geoldm_sampler_update": (C.c_int, [C.POINTER(Batch), C.c_int, fp, fp, fp, fp, fp, C.c_size_t, C.c_int,
                                         C.c_uint64, fp, fp, fp, fp]),

@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...) {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  float *h, *h2, *t1, *agg, *pq, *xa, *xb, *xagg;
+  float *h, *h2, *t1, *agg, *pq, *xa, *xb, *xagg, *dx;
   size_t bytes;
 };
 static Workspace carve(void* base, int n_node, int H) {
@@ -29,7 +29,7 @@ static Workspace carve(void* base, int n_node, int H) {
   };
   const size_t nh = (size_t)n_node * H;
   w.h = take(nh); w.h2 = take(nh); w.t1 = take(nh); w.agg = take(nh); w.pq = take(2 * nh);
-  w.xa = take((size_t)3 * n_node); w.xb = take((size_t)3 * n_node); w.xagg = take((size_t)3 * n_node);
+  w.xa = take((size_t)3 * n_node); w.xb = take((size_t)3 * n_node); w.xagg = take((size_t)3 * n_node); w.dx = take((size_t)3 * n_node);
   w.bytes = off;
   return w;
 }
@@ -64,8 +64,8 @@ static int check_cfg(const geoldm_egnn_config* cfg) {
 }
 
 int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights* w, const geoldm_batch* b,
-                        const float* h_in, const float* x_in, float* h_out, float* x_out, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        const float* h_in, const float* x_in, float* h_out, float* x_out, float* dx_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int N = b->n_node, H = cfg->hidden_nf;
@@ -94,8 +94,11 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
     if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
     cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
     if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, x_cur, x_in, ws.xagg, st))) return rc;
-    float* x_next = (l + 1 == cfg->n_layers) ? x_out : x_bufs[xi];
-    if ((rc = launch_coord_update(3 * N, x_cur, ws.xagg, cfg->agg_div, x_next, st))) return rc;
+    const bool last = (l + 1 == cfg->n_layers);
+    float* x_next = last ? x_out : x_bufs[xi];
+    float* dx_next = (last && dx_out) ? dx_out : ws.dx;   // dx is updated in place (elementwise)
+    if ((rc = launch_coord_update(3 * N, x_in, l == 0 ? nullptr : ws.dx, ws.xagg, cfg->agg_div, dx_next, x_next, st)))
+      return rc;
     x_cur = x_next;
     xi ^= 1;
   }

@@ -84,6 +84,7 @@ int launch_embed(int n_node, int H, int F, const float* h_in, const float* w, co
                  cudaStream_t st);
 int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, const float* b, float* out,
                    cudaStream_t st);
-int launch_coord_update(int n3, const float* x, const float* xagg, float div, float* x_next, cudaStream_t st);
+int launch_coord_update(int n3, const float* x0, const float* dx, const float* xagg, float div, float* dx_next,
+                        float* x_next, cudaStream_t st);
 
 }  // namespace geoldm

@@ -106,26 +106,31 @@ __global__ void outproj_kernel(int n_node, int H, int Fo, const float* __restric
   }
 }
 
-// x_next = x + xagg / div   (EquivariantUpdate: coord + agg, egnn_new.py:95-98)
-__global__ void coord_update_kernel(int n, const float* __restrict__ x, const float* __restrict__ xagg, float div,
+// EquivariantUpdate: coord + agg (egnn_new.py:95-98), kept as x0 + accumulated displacement:
+//   dx_next = dx + xagg / div ;  x_next = x0 + dx_next
+// The reference adds into x block after block and finally subtracts x0 again (egnn/models.py:80), which costs
+// ~ulp(|x|) of cancellation noise on a velocity that is 30x smaller than x; carrying the displacement keeps
+// the velocity at full precision (closer to the exact result, hence also closer to the reference: errors of
+// two fp32 evaluations add in quadrature).
+__global__ void coord_update_kernel(int n, const float* __restrict__ x0, const float* __restrict__ dx,
+                                    const float* __restrict__ xagg, float div, float* __restrict__ dx_next,
                                     float* __restrict__ x_next) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   float a = xagg[k];
   if (div != 1.0f) a = __fdiv_rn(a, div);
-  x_next[k] = __fadd_rn(x[k], a);
+  const float d = dx ? __fadd_rn(dx[k], a) : a;
+  dx_next[k] = d;
+  x_next[k] = __fadd_rn(x0[k], d);
 }
 
 // ---------------------------------------------------------------------------------------------
 // velocity, NaN guard, CoM projection
 // ---------------------------------------------------------------------------------------------
-__global__ void finish_a_kernel(int n3, const float* __restrict__ x_in, const float* __restrict__ x_final,
-                                int delta, float* __restrict__ vel, int* __restrict__ nan_flag) {
+__global__ void finish_a_kernel(int n3, const float* __restrict__ vel, int* __restrict__ nan_flag) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n3) return;
-  float v = delta ? __fsub_rn(x_final[k], x_in[k]) : x_final[k];
-  vel[k] = v;
-  if (isnan(v)) atomicOr(nan_flag, 1);
+  if (isnan(vel[k])) atomicOr(nan_flag, 1);
 }
 
 constexpr int MAX_PER_LANE = 8;  // molecules up to 256 atoms
@@ -298,11 +303,10 @@ int geoldm_dynamics_prep(const geoldm_batch* b, const int* node_src, const float
   return 0;
 }
 
-int geoldm_dynamics_finish_a(const geoldm_batch* b, const float* x_in, const float* x_final, int delta, float* vel,
-                             int* nan_flag, void* stream) {
+int geoldm_dynamics_finish_a(const geoldm_batch* b, const float* vel, int* nan_flag, void* stream) {
   const int n3 = 3 * b->n_node;
   if (n3 == 0) return 0;
-  finish_a_kernel<<<(n3 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n3, x_in, x_final, delta, vel, nan_flag);
+  finish_a_kernel<<<(n3 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n3, vel, nan_flag);
   GEOLDM_CHECK_LAUNCH("finish_a_kernel");
   return 0;
 }
@@ -379,9 +383,10 @@ int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, co
   GEOLDM_CHECK_LAUNCH("outproj_kernel");
   return 0;
 }
-int launch_coord_update(int n3, const float* x, const float* xagg, float div, float* x_next, cudaStream_t st) {
+int launch_coord_update(int n3, const float* x0, const float* dx, const float* xagg, float div, float* dx_next,
+                        float* x_next, cudaStream_t st) {
   if (n3 == 0) return 0;
-  coord_update_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(n3, x, xagg, div, x_next);
+  coord_update_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(n3, x0, dx, xagg, div, dx_next, x_next);
   GEOLDM_CHECK_LAUNCH("coord_update_kernel");
   return 0;
 }

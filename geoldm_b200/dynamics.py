@@ -71,24 +71,24 @@ class _EgnnWrapper(nn.Module):
         N = batch.n_node
         cb = batch.c_batch(egnn.tile_m())
         st = _stream(dev)
-        buf = self._buffers(N, dev)
+        buf = self._scratch(N, dev)
         src = batch.node_src if scatter else None
         _lib.check(L.geoldm_dynamics_prep(C.byref(cb), _lib.ptr(src), _lib.ptr(xh_flat), xh_dim, _lib.ptr(t_mol),
                                           _lib.ptr(t_table), _lib.ptr(step_idx), _lib.ptr(ctx_flat),
                                           self.context_node_nf if ctx_flat is not None else 0, int(condition_time),
                                           _lib.ptr(buf["h_in"]), egnn.in_node_nf, _lib.ptr(buf["x"]), st),
                    "geoldm_dynamics_prep")
-        egnn.forward(buf["h_in"], buf["x"], batch, h_out=buf["h_out"], x_out=buf["x_out"])
+        egnn.forward(buf["h_in"], buf["x"], batch, h_out=buf["h_out"], x_out=buf["x_out"], dx_out=buf["vel"])
+        vel = buf["vel"] if delta else buf["x_out"]      # dynamics: x_final - x ; decoder: x_final
         self.nan_flag.zero_()
-        _lib.check(L.geoldm_dynamics_finish_a(C.byref(cb), _lib.ptr(buf["x"]), _lib.ptr(buf["x_out"]), int(delta),
-                                              _lib.ptr(buf["vel"]), _lib.ptr(self.nan_flag), st),
+        _lib.check(L.geoldm_dynamics_finish_a(C.byref(cb), _lib.ptr(vel), _lib.ptr(self.nan_flag), st),
                    "geoldm_dynamics_finish_a")
-        _lib.check(L.geoldm_dynamics_finish_b(C.byref(cb), _lib.ptr(src), _lib.ptr(buf["vel"]), _lib.ptr(buf["h_out"]),
+        _lib.check(L.geoldm_dynamics_finish_b(C.byref(cb), _lib.ptr(src), _lib.ptr(vel), _lib.ptr(buf["h_out"]),
                                               egnn.out_node_nf, h_keep, _lib.ptr(self.nan_flag), _lib.ptr(out),
                                               out_dim, st), "geoldm_dynamics_finish_b")
         return out
 
-    def _buffers(self, N, dev):
+    def _scratch(self, N, dev):
         b = getattr(self, "_bufs", None)
         if b is None or b["N"] != N or b["x"].device != dev:
             e = self.egnn

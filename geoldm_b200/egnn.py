@@ -204,8 +204,9 @@ class EGNN(nn.Module):
 
     @torch.no_grad()
     def forward(self, h: torch.Tensor, x: torch.Tensor, batch: RaggedBatch, h_out: Optional[torch.Tensor] = None,
-                x_out: Optional[torch.Tensor] = None):
-        """h [N, in_node_nf], x [N, 3] ragged-packed fp32 CUDA tensors -> (h [N, out_node_nf], x [N, 3])."""
+                x_out: Optional[torch.Tensor] = None, dx_out: Optional[torch.Tensor] = None):
+        """h [N, in_node_nf], x [N, 3] ragged-packed fp32 CUDA tensors -> (h [N, out_node_nf], x [N, 3]).
+        dx_out (optional, [N, 3]) receives the accumulated coordinate displacement x_out - x at full precision."""
         if not (h.is_cuda and x.is_cuda):
             raise _lib.GeoldmError("EGNN.forward needs CUDA tensors (no CPU path)")
         N = batch.n_node
@@ -219,6 +220,7 @@ class EGNN(nn.Module):
         cb = batch.c_batch(self.tile_m())
         st = torch.cuda.current_stream(h.device).cuda_stream
         _lib.check(_lib.lib().geoldm_egnn_forward(C.byref(cfg), C.byref(w), C.byref(cb), _lib.ptr(h), _lib.ptr(x),
-                                                  _lib.ptr(h_out), _lib.ptr(x_out), _lib.ptr(ws), ws.numel(),
+                                                  _lib.ptr(h_out), _lib.ptr(x_out), _lib.ptr(dx_out), _lib.ptr(ws),
+                                                  ws.numel(),
                                                   C.c_void_p(st)), "geoldm_egnn_forward")
         return h_out, x_out

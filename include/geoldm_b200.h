@@ -109,7 +109,8 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
                         const float* h_in,  /* [N][in_node_nf] */
                         const float* x_in,  /* [N][3] */
                         float* h_out,       /* [N][out_node_nf] */
-                        float* x_out,       /* [N][3] final coordinates */
+                        float* x_out,       /* [N][3] final coordinates x_in + dx */
+                        float* dx_out,      /* [N][3] accumulated displacement sum_b agg_b (may be NULL) */
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- EGNN_dynamics_QM9._forward glue (egnn/models.py:56-76 and :80-113) ------------------- */
@@ -120,11 +121,11 @@ int geoldm_dynamics_prep(const geoldm_batch* b, const int* node_src, const float
                          const float* t_mol, const float* t_table, const int* step_idx_dev,
                          const float* context, int ctx_nf, int condition_time,
                          float* h_in, int in_node_nf, float* x, void* stream);
-/* vel = x_final - x_in (delta!=0) or x_final; drops time/context columns; NaN guard over the whole
- * batch (models.py:100-102); remove_mean_with_mask (utils.py:31-38); writes out[node_src[k]].
- * nan_flag: device int, must be zero on entry of geoldm_dynamics_finish_a. */
-int geoldm_dynamics_finish_a(const geoldm_batch* b, const float* x_in, const float* x_final, int delta,
-                             float* vel, int* nan_flag, void* stream);
+/* vel [N][3] = dx_out of geoldm_egnn_forward (dynamics: x_final - x, models.py:80) or x_out (decoder, :356).
+ * finish_a: NaN scan over the whole batch (models.py:100-102), nan_flag must be zero on entry.
+ * finish_b: zeroes vel if the flag is set, remove_mean_with_mask (utils.py:31-38), drops the time/context
+ * columns (keeps h_keep), writes out[node_src[k]] (node_src NULL: ragged output). */
+int geoldm_dynamics_finish_a(const geoldm_batch* b, const float* vel, int* nan_flag, void* stream);
 int geoldm_dynamics_finish_b(const geoldm_batch* b, const int* node_src, const float* vel, const float* h_out,
                              int h_stride, int h_keep, const int* nan_flag, float* out, int out_dim,
                              void* stream);

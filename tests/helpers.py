@@ -52,3 +52,32 @@ def build_cuda_model(cfg, sd, device="cuda", mma_mode="fp32"):
     assert not res.unexpected_keys, res.unexpected_keys
     assert all(k.startswith("vae.encoder") or k.endswith("buffer") for k in res.missing_keys), res.missing_keys
     return model.eval()
+
+
+def oracle64(cfg, sd, t, z, nodes, n_max, context=None, decoder=False):
+    """fp64 run of the oracle = the exact answer the fp32 implementations are noisy copies of."""
+    sd64 = O.cast_state_dict(sd, torch.float64)
+    nm, em = O.build_masks(list(nodes), n_max, torch.float64)
+    ctx = None if context is None else context.double()
+    with torch.no_grad():
+        if decoder:
+            dx, dh = O.decoder_forward(sd64, cfg, z.double(), nm, em, ctx)
+            return torch.cat([dx, dh], 2)
+        return O.dynamics_forward(sd64, cfg, t.double(), z.double(), nm, em, ctx)
+
+
+def assert_parity(tag, out, ref32, ref64, tol=1e-5):
+    """Well-posed form of north_star's "fp32 forward within 1e-5" (SURVEY §8c):
+      (1) against the exact (fp64) result of the same weights/inputs: err <= tol per part, and
+      (2) against the reference's fp32 output: err <= tol + err(ref32, fp64)   (triangle inequality: nobody can
+          be closer to the reference than the reference's own rounding noise unless it copies that noise; its
+          x part carries ~ulp(|x|)/|vel| of cancellation from vel = x_final - x, egnn/models.py:80).
+    """
+    out, ref32, ref64 = out.double().cpu(), ref32.double(), ref64.double()
+    ex64, eh64 = part_errors(out, ref64)
+    ex32, eh32 = part_errors(out, ref32)
+    fx, fh = part_errors(ref32, ref64)
+    print(f"[parity] {tag}: ours-vs-fp64 x {ex64:.2e} h {eh64:.2e} | ours-vs-ref32 x {ex32:.2e} h {eh32:.2e} | "
+          f"ref32-vs-fp64 (reference noise floor) x {fx:.2e} h {fh:.2e}")
+    assert ex64 < tol and eh64 < tol, (tag, "vs fp64", ex64, eh64)
+    assert ex32 < tol + fx and eh32 < tol + fh, (tag, "vs ref32", ex32, eh32, fx, fh)
