@@ -26,7 +26,7 @@ class _MaskCache:
     """node_mask -> RaggedBatch, keyed by storage identity (the sampler passes the same mask 1000x)."""
 
     def __init__(self):
-        self.key, self.batch = None, None
+        self.key, self.batch, self.hold = None, None, None
 
     def get(self, node_mask, edge_mask, validate=True) -> RaggedBatch:
         key = (node_mask.data_ptr(), tuple(node_mask.shape), node_mask._version,
@@ -34,6 +34,8 @@ class _MaskCache:
         if key != self.key:
             self.batch = pack_from_masks(node_mask, edge_mask, validate=validate)
             self.key = key
+            # strong refs: while they are alive their storage (hence data_ptr) cannot be handed to another mask
+            self.hold = (node_mask, edge_mask)
         return self.batch
 
 
