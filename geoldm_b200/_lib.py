@@ -24,11 +24,12 @@ class EgnnConfig(C.Structure):
 
 class EdgeMlp(C.Structure):
     _fields_ = [("pq_wt", fp), ("pq_b", fp), ("w_rd", fp), ("w2t", fp), ("b2", fp), ("w_out", fp), ("b_out", fp),
-                ("tc_pack", fp)]
+                ("tc_pack", fp), ("tc_pack_pq", fp)]
 
 
 class Gcl(C.Structure):
-    _fields_ = [("edge", EdgeMlp), ("node_w1t", fp), ("node_b1", fp), ("node_w2t", fp), ("node_b2", fp)]
+    _fields_ = [("edge", EdgeMlp), ("node_w1t", fp), ("node_b1", fp), ("node_w2t", fp), ("node_b2", fp),
+                ("tc_pack_node1", fp), ("tc_pack_node2", fp)]
 
 
 class Block(C.Structure):
@@ -63,6 +64,11 @@ _SIGS = {
     "geoldm_edge_equiv": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EdgeMlp), C.POINTER(Batch), fp, fp, fp, fp, fp]),
     "geoldm_linear": (C.c_int, [fp, C.c_int, fp, C.c_int, C.c_float, fp, fp, fp, C.c_int, fp, C.c_int, C.c_int,
                                 C.c_int, fp]),
+    "geoldm_tc_pack_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "geoldm_tc_pack": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
+    "geoldm_linear_tc": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, C.c_int,
+                                   fp, C.c_int, fp]),
+    "geoldm_tc_selftest": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_int, fp, fp, fp]),
     "geoldm_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, fp, C.c_int, fp]),
     "geoldm_decode": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp]),
 }

@@ -69,6 +69,9 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   if (int rc = check_cfg(cfg)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int N = b->n_node, H = cfg->hidden_nf;
+  const bool tcore = cfg->mma_mode != GEOLDM_MMA_FP32_SIMT;
+  const int terms = cfg->mma_mode == GEOLDM_MMA_TF32 ? 1 : 3;
+  GEOLDM_REQUIRE(cfg->mma_mode != GEOLDM_MMA_BF16, "mma_mode bf16 is not implemented yet");
   if (N == 0) return 0;
   Workspace ws = carve(workspace, N, H);
   GEOLDM_REQUIRE(workspace && workspace_bytes >= ws.bytes, "egnn_forward: workspace %zu < %zu bytes", workspace_bytes,
@@ -83,15 +86,28 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
     const geoldm_block& blk = w->block[l];
     for (int s = 0; s < cfg->inv_sublayers; ++s) {
       const geoldm_gcl& g = blk.gcl[s];
-      if ((rc = launch_linear(h, H, nullptr, 0, 1.f, g.edge.pq_wt, g.edge.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
+      if (tcore) {
+        if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, g.edge.tc_pack_pq, 2, g.edge.pq_b, nullptr, 0, ws.pq, N, st))) return rc;
+      } else {
+        if ((rc = launch_linear(h, H, nullptr, 0, 1.f, g.edge.pq_wt, g.edge.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
+      }
       cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
       if ((rc = edge_dispatch(*cfg, g.edge, *b, false, ws.pq, x_cur, x_in, ws.agg, st))) return rc;
-      if ((rc = launch_linear(h, H, ws.agg, H, cfg->agg_div, g.node_w1t, g.node_b1, nullptr, 1, ws.t1, N, H, st))) return rc;
-      if ((rc = launch_linear(ws.t1, H, nullptr, 0, 1.f, g.node_w2t, g.node_b2, h, 2, h2, N, H, st))) return rc;
+      if (tcore) {
+        if ((rc = launch_linear_tc(H, terms, h, H, ws.agg, H, cfg->agg_div, g.tc_pack_node1, 1, g.node_b1, nullptr, 1, ws.t1, N, st))) return rc;
+        if ((rc = launch_linear_tc(H, terms, ws.t1, H, nullptr, 0, 1.f, g.tc_pack_node2, 1, g.node_b2, h, 2, h2, N, st))) return rc;
+      } else {
+        if ((rc = launch_linear(h, H, ws.agg, H, cfg->agg_div, g.node_w1t, g.node_b1, nullptr, 1, ws.t1, N, H, st))) return rc;
+        if ((rc = launch_linear(ws.t1, H, nullptr, 0, 1.f, g.node_w2t, g.node_b2, h, 2, h2, N, H, st))) return rc;
+      }
       float* tmp = h; h = h2; h2 = tmp;
     }
     const geoldm_edge_mlp& e = blk.equiv;
-    if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
+    if (tcore) {
+      if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, e.tc_pack_pq, 2, e.pq_b, nullptr, 0, ws.pq, N, st))) return rc;
+    } else {
+      if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
+    }
     cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
     if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, x_cur, x_in, ws.xagg, st))) return rc;
     const bool last = (l + 1 == cfg->n_layers);
@@ -121,6 +137,18 @@ int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div
                   const float* res, int epi, float* out, int m, int n, int mma_mode, void* stream) {
   (void)mma_mode;
   return launch_linear(a1, k1, a2, k2, a2_div, wt, bias, res, epi, out, m, n, (cudaStream_t)stream);
+}
+
+
+int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
+                     const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out, int m,
+                     void* stream) {
+  return launch_linear_tc(H, terms, a1, k1, a2, k2, a2_div, w_pack, n_blocks, bias, res, epi, out, m,
+                          (cudaStream_t)stream);
+}
+int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, const int* tile_row, int n_tile, int n_rows,
+                       const void* w_pack, float* out, void* stream) {
+  return launch_tc_selftest(H, terms, a, src_row, tile_row, n_tile, n_rows, w_pack, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -135,7 +135,7 @@ class EGNN(nn.Module):
     @torch.no_grad()
     def packed(self):
         """(ctypes EgnnWeights, keep-alive list).  Rebuilt when any parameter changed."""
-        key = self._params_key()
+        key = (self._params_key(), self.mma_mode)
         if self._pack is not None and key == self._pack_key:
             return self._pack
         H = self.hidden_nf
@@ -148,6 +148,24 @@ class EGNN(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
+        mode = _lib.MMA_MODES[self.mma_mode] if isinstance(self.mma_mode, str) else int(self.mma_mode)
+        tcore = mode != _lib.MMA_FP32_SIMT
+        L = _lib.lib()
+        stream = C.c_void_p(torch.cuda.current_stream(self.embedding.weight.device).cuda_stream) \
+            if self.embedding.weight.is_cuda else None
+
+        def tc_pack(wmat):
+            """[n_out, k] Linear weight -> tensor-core operand pack (tf32 hi/lo, SWIZZLE_128B k-slabs)."""
+            if not tcore:
+                return None
+            wmat = wmat.detach().to(torch.float32).contiguous()
+            n_out, k = wmat.shape
+            buf = torch.empty(L.geoldm_tc_pack_bytes(H, n_out, k), dtype=torch.uint8, device=wmat.device)
+            _lib.check(L.geoldm_tc_pack(H, _lib.ptr(wmat), n_out, k, _lib.ptr(buf), stream), "geoldm_tc_pack")
+            keep.append(wmat)
+            keep.append(buf)
+            return buf.data_ptr()
+
         def edge(first, second, head, head_bias):
             w1 = first.weight                                    # [H, 2H+2]
             e = _lib.EdgeMlp()
@@ -158,7 +176,8 @@ class EGNN(nn.Module):
             e.b2 = dev(second.bias)
             e.w_out = dev(head.weight.reshape(H)) if head is not None else dev(torch.zeros(H, device=w1.device))
             e.b_out = dev(head_bias.reshape(1)) if head_bias is not None else None
-            e.tc_pack = None
+            e.tc_pack = tc_pack(second.weight)
+            e.tc_pack_pq = tc_pack(torch.cat([w1[:, :H], w1[:, H:2 * H]], dim=0))      # [2H, H]: block 0 -> P, 1 -> Q
             return e
 
         w = _lib.EgnnWeights()
@@ -173,6 +192,8 @@ class EGNN(nn.Module):
                 cg.edge = edge(g.edge_mlp[0], g.edge_mlp[2], att, att.bias if att is not None else None)
                 cg.node_w1t, cg.node_b1 = dev(g.node_mlp[0].weight.t()), dev(g.node_mlp[0].bias)
                 cg.node_w2t, cg.node_b2 = dev(g.node_mlp[2].weight.t()), dev(g.node_mlp[2].bias)
+                cg.tc_pack_node1 = tc_pack(g.node_mlp[0].weight)
+                cg.tc_pack_node2 = tc_pack(g.node_mlp[2].weight)
             q = blk.gcl_equiv
             w.block[b].equiv = edge(q.coord_mlp[0], q.coord_mlp[2], q.coord_mlp[4], None)
         self._pack, self._pack_key = (w, keep), key

@@ -63,7 +63,8 @@ typedef struct {
   const float* b2;           /* [H]                                                         */
   const float* w_out;        /* [H]      att_mlp.0.weight  |  coord_mlp.4.weight            */
   const float* b_out;        /* [1]      att_mlp.0.bias    |  NULL                          */
-  const void* tc_pack;       /* mode-specific tensor-core operand pack of w2 (or NULL)      */
+  const void* tc_pack;       /* tensor-core pack of the second layer  (geoldm_tc_pack_bytes(H, H, H))   */
+  const void* tc_pack_pq;    /* tensor-core pack of the split first layer, 2 column blocks of H          */
 } geoldm_edge_mlp;
 
 typedef struct {
@@ -72,6 +73,8 @@ typedef struct {
   const float* node_b1;      /* [H]                                                         */
   const float* node_w2t;     /* [H][H]   node_mlp.2 transposed                              */
   const float* node_b2;      /* [H]                                                         */
+  const void* tc_pack_node1; /* tensor-core pack of node_mlp.0 (K = 2H)                     */
+  const void* tc_pack_node2; /* tensor-core pack of node_mlp.2 (K = H)                      */
 } geoldm_gcl;
 
 typedef struct {
@@ -157,6 +160,19 @@ int geoldm_edge_equiv(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, c
 int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt,
                   const float* bias, const float* res, int epi, float* out, int m, int n, int mma_mode,
                   void* stream);
+/* Tensor-core operand pack of a weight matrix W [n_out][k] (row-major, PyTorch Linear layout) for the tcgen05
+ * kernels: n_out/H column blocks x k/32 k-slabs x {tf32-hi, tf32-lo} images of H rows x 128 bytes in the canonical
+ * SWIZZLE_128B K-major order (the exact bytes the TMA engine drops into shared memory).  Runs on `stream`. */
+size_t geoldm_tc_pack_bytes(int H, int n_out, int k);
+int geoldm_tc_pack(int H, const float* w, int n_out, int k, void* pack, void* stream);
+/* same contract as geoldm_linear with n = n_blocks*H outputs, on the tensor cores; terms: 3 = 3xTF32, 1 = TF32 */
+int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
+                     const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out,
+                     int m, void* stream);
+/* descriptor / swizzle / pipeline self-test: out[row][0:H] = sum_k a[src_row[row]][k] * W[:, k] with a row stride
+ * of 2H floats (the P|Q layout), rows split into tiles by tile_row like the edge kernels */
+int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, const int* tile_row, int n_tile,
+                       int n_rows, const void* w_pack, float* out, void* stream);
 /* Philox4x32-10 standard normals (Box-Muller), the sampler's noise stream exposed for tests:
  * out[4*d+e] = e-th normal of block counter=(d, node, blk, seed>>32), key=(mol_id, (uint32)seed), i.e. what
  * geoldm_sampler_update draws for draw index d, node `node` of molecule `mol_id`, columns 4*blk+e. */

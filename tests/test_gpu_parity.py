@@ -71,12 +71,74 @@ def test_linear_kernel(dev, m, k1, k2, n, epi):
     assert O.err_metric(out.cpu().double(), ref) < 2e-6
 
 
+@pytest.mark.parametrize("H", [256, 64, 192, 128])
+@pytest.mark.parametrize("terms", [3, 1])
+def test_tc_selftest_gemm(dev, H, terms):
+    """tcgen05 descriptors / SWIZZLE_128B images / mbarrier pipeline: out = A[src_row] * W^T on ragged tiles."""
+    if not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    from geoldm_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(H + terms)
+    n_src, n_rows = 97, 128 * 5 + 77
+    a = torch.randn(n_src, 2 * H, generator=g)
+    w = torch.randn(H, H, generator=g) / np.sqrt(H)
+    src = torch.randint(0, n_src, (n_rows,), generator=g, dtype=torch.int32)
+    bounds = [0, 128, 131, 259, 387, 400, 528, 656, n_rows]          # ragged tiles (<= 128 rows each)
+    tile_row = torch.tensor(bounds, dtype=torch.int32)
+    ad, wd, sd_, td = a.to(dev), w.to(dev), src.to(dev), tile_row.to(dev)
+    pack = torch.empty(L.geoldm_tc_pack_bytes(H, H, H), dtype=torch.uint8, device=dev)
+    _lib.check(L.geoldm_tc_pack(H, _lib.ptr(wd), H, H, _lib.ptr(pack), None), "pack")
+    out = torch.zeros(n_rows, H, device=dev)
+    _lib.check(L.geoldm_tc_selftest(H, terms, _lib.ptr(ad), _lib.ptr(sd_), _lib.ptr(td), len(bounds) - 1, n_rows,
+                                    _lib.ptr(pack), _lib.ptr(out), None), "selftest")
+    torch.cuda.synchronize()
+    ref = a[src.long(), :H].double() @ w.double().T
+    err = O.err_metric(out.cpu().double(), ref)
+    print(f"[tc selftest] H={H} terms={terms}: err {err:.2e}")
+    assert err < (5e-6 if terms == 3 else 2e-3), err
+
+
+@pytest.mark.parametrize("m,k1,k2,nb,epi,H", [(1154, 256, 0, 2, 0, 256), (1154, 256, 256, 1, 1, 256),
+                                               (333, 192, 0, 1, 2, 192), (77, 64, 64, 1, 1, 64), (128, 128, 0, 2, 0, 128)])
+def test_linear_tc_kernel(dev, m, k1, k2, nb, epi, H):
+    if not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    from geoldm_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    n = nb * H
+    a1 = torch.randn(m, k1, generator=g)
+    a2 = torch.randn(m, k2, generator=g) if k2 else None
+    w = torch.randn(n, k1 + k2, generator=g) / np.sqrt(k1 + k2)
+    bias = torch.randn(n, generator=g)
+    res = torch.randn(m, n, generator=g)
+    div = 3.0 if k2 else 1.0
+    a = a1 if a2 is None else torch.cat([a1, a2 / div], 1)
+    ref = a.double() @ w.double().T + bias.double()
+    if epi == 1:
+        ref = torch.nn.functional.silu(ref)
+    if epi == 2:
+        ref = ref + res.double()
+    d = lambda t: None if t is None else t.to(dev)
+    A1, A2, W, B, R = d(a1), d(a2), d(w), d(bias), d(res)
+    pack = torch.empty(L.geoldm_tc_pack_bytes(H, n, k1 + k2), dtype=torch.uint8, device=dev)
+    _lib.check(L.geoldm_tc_pack(H, _lib.ptr(W), n, k1 + k2, _lib.ptr(pack), None), "pack")
+    out = torch.empty(m, n, device=dev)
+    _lib.check(L.geoldm_linear_tc(H, 3, _lib.ptr(A1), k1, _lib.ptr(A2), k2, div, _lib.ptr(pack), nb, _lib.ptr(B),
+                                  _lib.ptr(R), epi, _lib.ptr(out), m, None), "linear_tc")
+    torch.cuda.synchronize()
+    err = O.err_metric(out.cpu().double(), ref)
+    print(f"[linear_tc] m={m} k={k1}+{k2} n={n} epi={epi}: err {err:.2e}")
+    assert err < 5e-6
+
+
 @pytest.mark.parametrize("H,nodes", [(256, [29, 3, 17, 18, 5]), (64, [9, 2, 1, 30]), (192, [12, 25]), (32, [70, 4])])
 @pytest.mark.parametrize("mode", ["fp32", "3xtf32"])
 def test_edge_kernels_vs_oracle(dev, H, nodes, mode):
     """geoldm_edge_gcl / geoldm_edge_equiv vs the oracle's edge_model + unsorted_segment_sum."""
-    if mode != "fp32" and not _has_tc():
-        pytest.skip("tcgen05 kernels not built")
+    if mode != "fp32" and (not _has_tc() or H == 32):
+        pytest.skip("tcgen05 kernels not built / H=32 unsupported on the tensor-core path")
     from geoldm_b200 import _lib
     from geoldm_b200.egnn import EGNN, TILE_M
     from geoldm_b200.packing import pack_molecules
@@ -117,15 +179,20 @@ def test_edge_kernels_vs_oracle(dev, H, nodes, mode):
     pq = torch.empty(N, 2 * H, device=dev)
     for which, ref in (("gcl", agg_ref), ("equiv", xagg_ref)):
         em = w.block[0].gcl[0].edge if which == "gcl" else w.block[0].equiv
-        _lib.check(L.geoldm_linear(_lib.ptr(hd), H, None, 0, 1.0, em.pq_wt, em.pq_b, None, 0, _lib.ptr(pq), N, 2 * H,
-                                   cfgc.mma_mode, None), "linear")
+        if mode == "fp32":
+            _lib.check(L.geoldm_linear(_lib.ptr(hd), H, None, 0, 1.0, em.pq_wt, em.pq_b, None, 0, _lib.ptr(pq), N, 2 * H,
+                                       cfgc.mma_mode, None), "linear")
+        else:
+            _lib.check(L.geoldm_linear_tc(H, 3, _lib.ptr(hd), H, None, 0, 1.0, em.tc_pack_pq, 2, em.pq_b, None, 0,
+                                          _lib.ptr(pq), N, None), "linear_tc")
         out = torch.zeros(N, H if which == "gcl" else 3, device=dev)
         fn = L.geoldm_edge_gcl if which == "gcl" else L.geoldm_edge_equiv
         _lib.check(fn(C.byref(cfgc), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xd), _lib.ptr(x0d), _lib.ptr(out),
                       None), which)
         torch.cuda.synchronize()
         err = O.err_metric(out.cpu(), ref)
-        assert err < 3e-6, (which, err)
+        print(f"[edge kernel] H={H} mode={mode} {which}: err {err:.2e}")
+        assert err < (3e-6 if mode == "fp32" else 6e-6), (which, err)
 
 
 # ---------------------------------------------------------------------------------------------------
