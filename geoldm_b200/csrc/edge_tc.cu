@@ -12,15 +12,22 @@
 //              epilogue: out = epi(D + bias) (+ residual)
 //   MODE_RAW   A[row][k] = P_{edge_i[row]}[k], epilogue dumps D  (self-test of descriptors / swizzle / pipeline)
 //
-// Roles (320 threads, 1 CTA per SM, ~214 KB shared memory, all 512 TMEM columns):
-//   warps 0-3  epilogue  : tcgen05.ld of the fp32 accumulator (thread = TMEM lane = edge row), fused tail
-//   warps 4-7  producers : generate the A k-slab (32 columns) straight into the canonical SWIZZLE_128B K-major
-//                          shared-memory layout as tf32 hi / lo images; fence.proxy.async; mbarrier arrive
-//   warp  8    loader    : cp.async.bulk (TMA engine) of the pre-swizzled hi|lo W k-slab, mbarrier complete_tx
-//   warp  9    MMA       : one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=H, K=8) x 4 k-steps x 3
-//                          terms per slab, tcgen05.commit releases the shared-memory stages / publishes D
-// Pipelines: W slabs 2 stages, A slabs 2 stages, accumulators 2 x 256 TMEM columns (epilogue of tile t overlaps
-// the MMAs of tile t+1).  No N^2 x nf tensor and no pre-activation ever reaches HBM.
+// Roles (576 threads, 1 CTA per SM, ~200 KB shared memory, all 512 TMEM columns):
+//   warps 0-7   epilogue  : tcgen05.ld of the fp32 accumulator; thread = (TMEM lane = edge row, column half);
+//                           fused tail (bias, SiLU, head dot, gate, transposing segment sum, atomics)
+//   warps 8-15  producers : generate the A k-slab (32 columns) straight into the canonical SWIZZLE_128B K-major
+//                           shared-memory layout as tf32 hi / lo images; fence.proxy.async; mbarrier arrive
+//   warp  16    loader    : cp.async.bulk (TMA engine) of the pre-swizzled hi|lo W stage, mbarrier complete_tx
+//   warp  17    MMA       : one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=H/2, K=8) x 4 k-steps x 3
+//                           terms per stage, tcgen05.commit releases the shared-memory stages / publishes D
+// Pipelines: W stages = (k-slab, N-half) x 4, multicast across a cluster of CS CTAs (each CTA fetches 1/CS of a
+// stage and the TMA engine writes it into every CTA of the cluster: L2->SM weight traffic / CS); A slabs 2 stages.
+// TMEM: the K reduction of a tile is split in two halves accumulated in two 256-column regions (half the magnitude
+// and half the number of round-toward-zero accumulations each); the epilogue first folds region 0 into region 1
+// with a rounded fp32 add and releases region 0 at once, so the next tile's first K-half overlaps the fused tail of
+// the current one.  No N^2 x nf tensor and no pre-activation ever reaches HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,7 +37,10 @@ using namespace tc;
 
 constexpr int TM = 128;         // rows per tile (TMEM lanes)
 constexpr int BK = 32;          // k-slab: 32 fp32/tf32 = 128 bytes per row = one swizzle row
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 576;    // 8 epilogue + 8 producer warps + loader + MMA
+constexpr int NWS = 3;          // W pipeline stages
+constexpr int EPI_T = 256, PROD_T = 256;
+constexpr int WARP_LOAD = 16, WARP_MMA = 17;
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
 
 struct TcArgs {
@@ -71,131 +81,171 @@ constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;
 
 template <int H>
 struct Smem {
-  static constexpr uint32_t W_STAGE = 2u * H * 128u;          // hi + lo
+  static constexpr uint32_t NH = H / 2;                       // W rows (= output columns) per stage
+  static constexpr uint32_t W_IMG = NH * 128u;                // one tf32 image of a stage
+  static constexpr uint32_t W_STAGE = 2u * W_IMG;             // hi + lo
   static constexpr uint32_t A_STAGE = 2u * TM * 128u;         // hi + lo
   static constexpr uint32_t OFF_W = 0;
-  static constexpr uint32_t OFF_A = OFF_W + 2 * W_STAGE;
-  static constexpr uint32_t OFF_T = OFF_A + 2 * A_STAGE;      // [128][32] fp32 transposition tile
-  static constexpr uint32_t OFF_SI = OFF_T + TM * 32 * 4;     // int   [128] receiver per row
+  static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
+  static constexpr uint32_t OFF_T = OFF_A + 2 * A_STAGE;      // [2][128][32] fp32 transposition tiles (one per column half)
+  static constexpr uint32_t OFF_SI = OFF_T + 2 * TM * 32 * 4; // int   [128] receiver per row
   static constexpr uint32_t OFF_PS = OFF_SI + TM * 4;         // int   [129] piece starts
   static constexpr uint32_t OFF_DX = OFF_PS + (TM + 4) * 4;   // float [128][4] equiv deltas
-  static constexpr uint32_t OFF_CNT = OFF_DX + TM * 16;       // int   [8]
-  static constexpr uint32_t OFF_BAR = OFF_CNT + 32;           // 12 mbarriers
-  static constexpr uint32_t OFF_TMEM = OFF_BAR + 12 * 8;
+  static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;       // float [2][128] row-dot partials of the two column halves
+  static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;   // float [2][H] staged bias / head vectors
+  static constexpr uint32_t OFF_CNT = OFF_VEC + 2 * H * 4;    // int   [8]
+  static constexpr uint32_t OFF_BAR = OFF_CNT + 32;           // 2*NWS + 8 mbarriers
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + (2 * NWS + 8) * 8;
   static constexpr uint32_t BYTES = OFF_TMEM + 16;
   static constexpr uint32_t ALLOC = BYTES + 1024;             // slack for manual 1024-byte alignment
 };
 
-template <int H, int MODE>
+template <int H, int MODE, int CS>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   using S = Smem<H>;
+  constexpr int NH = H / 2;
   extern __shared__ uint8_t smem_raw[];
+  // same offset in every CTA of the cluster (multicast writes and barrier arrives address peers by offset)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* w_full = bars;          // [2]
-  uint64_t* w_empty = bars + 2;     // [2]
-  uint64_t* a_full = bars + 4;      // [2]
-  uint64_t* a_empty = bars + 6;     // [2]
-  uint64_t* acc_full = bars + 8;    // [2]
-  uint64_t* acc_empty = bars + 10;  // [2]
+  uint64_t* w_full = bars;                    // [NWS]
+  uint64_t* w_empty = bars + NWS;             // [NWS]
+  uint64_t* a_full = bars + 2 * NWS;          // [2]
+  uint64_t* a_empty = bars + 2 * NWS + 2;     // [2]
+  uint64_t* acc_full = bars + 2 * NWS + 4;    // [2]  K-half 0 / 1 of the current tile complete
+  uint64_t* acc_empty = bars + 2 * NWS + 6;   // [2]  TMEM region 0 / 1 drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int total_work = a.n_tile * a.n_blocks;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+  // work items: (tile, column block); padded so that all CTAs of a cluster run the same number of iterations on
+  // the same column block (they share the W stream); padding tiles have zero rows
+  const int n_tile_pad = (a.n_tile + CS - 1) / CS * CS;
+  const int total_work = n_tile_pad * a.n_blocks;
+  const int n_iter = (total_work + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int half_slabs = a.n_slabs / 2;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NWS; ++s) {
       mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
-      mbar_init(&a_full[s], 128);
+      mbar_init(&w_empty[s], CS);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], PROD_T);
       mbar_init(&a_empty[s], 1);
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
+      mbar_init(&acc_empty[s], EPI_T);
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == WARP_MMA) tmem_alloc(tmem_slot, 512);
+  if (MODE == MODE_GCL || MODE == MODE_EQUIV) {     // stage the per-column vectors of the fused tail
+    float* vec = reinterpret_cast<float*>(smem + S::OFF_VEC);
+    for (int c = tid; c < H; c += NTHREADS) { vec[c] = a.b2[c]; vec[H + c] = a.w_out[c]; }
+  }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();             // peers' barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    // =========================== W-slab loader (TMA engine) ===========================================
+  auto tile_of = [&](int iter, int& tile, int& nb, int& row0, int& nrows) {
+    const int work = iter * (int)gridDim.x + (int)blockIdx.x;
+    nb = work / n_tile_pad;
+    tile = work % n_tile_pad;
+    if (nb >= a.n_blocks || tile >= a.n_tile) {   // padding
+      nb = nb >= a.n_blocks ? a.n_blocks - 1 : nb;
+      row0 = 0; nrows = 0;
+      return;
+    }
+    row0 = a.tile_row ? a.tile_row[tile] : tile * TM;
+    nrows = (a.tile_row ? a.tile_row[tile + 1] : min(a.n_rows, row0 + TM)) - row0;
+  };
+
+  if (warp == WARP_LOAD) {
+    // =========================== W-stage loader (TMA engine, multicast) ===================================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const int nb = work % a.n_blocks;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_pack) + (size_t)nb * a.n_slabs * S::W_STAGE;
-        for (int s = 0; s < a.n_slabs; ++s, ++it) {
-          const int st = it & 1;
-          mbar_wait(&w_empty[st], ((it >> 1) & 1) ^ 1);
+      uint32_t wit = 0;
+      for (int iter = 0; iter < n_iter; ++iter) {
+        int tile, nb, row0, nrows;
+        tile_of(iter, tile, nb, row0, nrows);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_pack) + (size_t)nb * a.n_slabs * 2 * S::W_STAGE;
+        for (int s = 0; s < 2 * a.n_slabs; ++s, ++wit) {       // (slab, N-half) stages
+          const int st = wit % NWS;
+          mbar_wait(&w_empty[st], ((wit / NWS) & 1) ^ 1);       // every CTA of the cluster released the stage
           mbar_arrive_expect_tx(&w_full[st], S::W_STAGE);
-          uint8_t* dst = smem + S::OFF_W + st * S::W_STAGE;
-          const uint8_t* g = src + (size_t)s * S::W_STAGE;
-#pragma unroll
-          for (uint32_t off = 0; off < S::W_STAGE; off += 16384)
-            bulk_g2s(dst + off, g + off, (S::W_STAGE - off) < 16384 ? (S::W_STAGE - off) : 16384, &w_full[st]);
+          constexpr uint32_t PART = S::W_STAGE / CS;
+          uint8_t* dst = smem + S::OFF_W + st * S::W_STAGE + crank * PART;
+          const uint8_t* g = src + (size_t)s * S::W_STAGE + crank * PART;
+          if (CS > 1) bulk_g2s_multicast(dst, g, PART, &w_full[st], cmask);
+          else bulk_g2s(dst, g, PART, &w_full[st]);
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ==============================================================
-    const uint32_t idesc = make_idesc_tf32(H);
-    uint32_t it = 0, tcount = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++tcount) {
-      const int acc = tcount & 1;
-      mbar_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
-      for (int s = 0; s < a.n_slabs; ++s, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&w_full[st], ph);
-        mbar_wait(&a_full[st], ph);
+    const uint32_t idesc = make_idesc_tf32(NH);
+    uint32_t wit = 0, ait = 0;
+    for (int iter = 0; iter < n_iter; ++iter) {
+      for (int kh = 0; kh < 2; ++kh) {
+        mbar_wait(&acc_empty[kh], (iter & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = smem_u32(smem + S::OFF_A + st * S::A_STAGE);
-          const uint32_t a_lo = a_hi + TM * 128;
-          const uint32_t w_hi = smem_u32(smem + S::OFF_W + st * S::W_STAGE);
-          const uint32_t w_lo = w_hi + H * 128;
+        const uint32_t d_tmem = tmem_base + kh * 256;
+        for (int s = 0; s < half_slabs; ++s, ++ait) {
+          const int ast = ait & 1;
+          mbar_wait(&a_full[ast], (ait >> 1) & 1);
+          for (int nh = 0; nh < 2; ++nh, ++wit) {
+            const int wst = wit % NWS;
+            mbar_wait(&w_full[wst], (wit / NWS) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_hi = smem_u32(smem + S::OFF_A + ast * S::A_STAGE);
+              const uint32_t a_lo = a_hi + TM * 128;
+              const uint32_t w_hi = smem_u32(smem + S::OFF_W + wst * S::W_STAGE);
+              const uint32_t w_lo = w_hi + S::W_IMG;
+              const uint32_t d = d_tmem + nh * NH;
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t da_hi = make_smem_desc_sw128(a_hi + kk * 32), da_lo = make_smem_desc_sw128(a_lo + kk * 32);
-            const uint64_t dw_hi = make_smem_desc_sw128(w_hi + kk * 32), dw_lo = make_smem_desc_sw128(w_lo + kk * 32);
-            if (a.terms == 3) {
-              mma_tf32(d_tmem, da_lo, dw_hi, idesc, (s | kk) != 0);
-              mma_tf32(d_tmem, da_hi, dw_lo, idesc, 1);
-              mma_tf32(d_tmem, da_hi, dw_hi, idesc, 1);
-            } else {
-              mma_tf32(d_tmem, da_hi, dw_hi, idesc, (s | kk) != 0);
+              for (int kk = 0; kk < BK / 8; ++kk) {
+                const uint64_t da_hi = make_smem_desc_sw128(a_hi + kk * 32), da_lo = make_smem_desc_sw128(a_lo + kk * 32);
+                const uint64_t dw_hi = make_smem_desc_sw128(w_hi + kk * 32), dw_lo = make_smem_desc_sw128(w_lo + kk * 32);
+                if (a.terms == 3) {
+                  mma_tf32(d, da_lo, dw_hi, idesc, (s | kk) != 0);
+                  mma_tf32(d, da_hi, dw_lo, idesc, 1);
+                  mma_tf32(d, da_hi, dw_hi, idesc, 1);
+                } else {
+                  mma_tf32(d, da_hi, dw_hi, idesc, (s | kk) != 0);
+                }
+              }
+              if (CS > 1) mma_commit_multicast(&w_empty[wst], cmask);
+              else mma_commit(&w_empty[wst]);
+              if (nh == 1) {
+                mma_commit(&a_empty[ast]);
+                if (s == half_slabs - 1) mma_commit(&acc_full[kh]);
+              }
             }
+            __syncwarp();
           }
-          mma_commit(&w_empty[st]);
-          mma_commit(&a_empty[st]);
-          if (s == a.n_slabs - 1) mma_commit(&acc_full[acc]);
         }
-        __syncwarp();
       }
     }
-  } else if (warp >= 4) {
-    // =========================== A producers (128 threads) ==============================================
-    const int pt = tid - 128;
+  } else if (warp >= 8) {
+    // =========================== A producers (256 threads) ==============================================
+    const int pt = tid - EPI_T;
     const int chunk = pt & 7;        // 16-byte chunk: k = 4*chunk .. 4*chunk+3 inside the slab
-    const int rbase = pt >> 3;       // rows rbase + 16 p
+    const int rbase = pt >> 3;       // rows rbase + 32 p
     uint32_t it = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-      const int tile = work / a.n_blocks;
-      const int row0 = a.tile_row ? a.tile_row[tile] : tile * TM;
-      const int nrows = (a.tile_row ? a.tile_row[tile + 1] : min(a.n_rows, row0 + TM)) - row0;
-      const float* pP[8];
-      const float* pQ[8];
-      float rr[8], dd[8];
-      bool valid[8];
+    for (int iter = 0; iter < n_iter; ++iter) {
+      int tile, nb, row0, nrows;
+      tile_of(iter, tile, nb, row0, nrows);
+      const float* pP[4];
+      const float* pQ[4];
+      float rr[4], dd[4];
+      bool valid[4];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int r = rbase + 16 * p;
+      for (int p = 0; p < 4; ++p) {
+        const int r = rbase + 32 * p;
         valid[p] = r < nrows;
         pP[p] = nullptr; pQ[p] = nullptr; rr[p] = 0.f; dd[p] = 0.f;
         if (valid[p]) {
@@ -218,11 +268,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       for (int s = 0; s < a.n_slabs; ++s, ++it) {
         const int st = it & 1;
         const int k0 = s * BK;
-        float4 v[8];
-        float4 q[8];
+        float4 v[4];
+        float4 q[4];
         // issue the global loads first; they are in flight while we wait for the stage to drain
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
+        for (int p = 0; p < 4; ++p) {
           v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
           q[p] = v[p];
           if (valid[p]) {
@@ -244,8 +294,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         uint8_t* a_hi = smem + S::OFF_A + st * S::A_STAGE;
         uint8_t* a_lo = a_hi + TM * 128;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int r = rbase + 16 * p;
+        for (int p = 0; p < 4; ++p) {
+          const int r = rbase + 32 * p;
           float e[4];
           if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
             e[0] = silu(fmaf(wd.x, dd[p], fmaf(wr.x, rr[p], v[p].x + q[p].x)));
@@ -279,58 +329,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       }
     }
   } else {
-    // =========================== epilogue (warps 0-3, thread = TMEM lane = row) ===========================
-    const int r = tid;  // 0..127
-    float* T = reinterpret_cast<float*>(smem + S::OFF_T);
+    // ============= epilogue (warps 0-7: thread = (TMEM lane = row, column half)) ==========================
+    const int r = (warp & 3) * 32 + lane;   // row / TMEM lane; a warp may only touch lanes 32*(warp%4)..+31
+    const int hf = warp >> 2;               // column half handled by this thread
+    constexpr int HC = H / 2;               // columns per half
+    constexpr int NCH = HC / 32;            // 32-column chunks per half
+    const int et = tid;                     // 0..255
+    float* T = reinterpret_cast<float*>(smem + S::OFF_T) + hf * TM * 32;
     int* s_i = reinterpret_cast<int*>(smem + S::OFF_SI);
     int* s_ps = reinterpret_cast<int*>(smem + S::OFF_PS);
     float* s_dx = reinterpret_cast<float*>(smem + S::OFF_DX);
+    float* s_dot = reinterpret_cast<float*>(smem + S::OFF_DOT);
+    const float* s_b2 = reinterpret_cast<const float*>(smem + S::OFF_VEC) + hf * HC;
+    const float* s_wo = s_b2 + H;
     int* s_cnt = reinterpret_cast<int*>(smem + S::OFF_CNT);
-    uint32_t tcount = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++tcount) {
-      const int tile = work / a.n_blocks, nb = work % a.n_blocks;
-      const int row0 = a.tile_row ? a.tile_row[tile] : tile * TM;
-      const int nrows = (a.tile_row ? a.tile_row[tile + 1] : min(a.n_rows, row0 + TM)) - row0;
+    const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * HC;
+    for (int iter = 0; iter < n_iter; ++iter) {
+      int tile, nb, row0, nrows;
+      tile_of(iter, tile, nb, row0, nrows);
       const bool valid = r < nrows;
-      const int acc = tcount & 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256;
       int my_i = -1;
       float ux = 0.f, uy = 0.f, uz = 0.f;
       if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
         if (valid) {
           my_i = a.edge_i[row0 + r];
-          if (MODE == MODE_EQUIV) {
+          if (MODE == MODE_EQUIV && hf == 0) {
             EdgeGeom g = edge_geom(a.x, a.x0, my_i, a.edge_j[row0 + r], a.norm_constant);
             ux = g.ux; uy = g.uy; uz = g.uz;
           }
         }
-        s_i[r] = my_i;
+        if (hf == 0) s_i[r] = my_i;
       }
-      mbar_wait(&acc_full[acc], (tcount >> 1) & 1);
+      const uint32_t ph = iter & 1;
+      mbar_wait(&acc_full[0], ph);
+      mbar_wait(&acc_full[1], ph);
       tc_fence_after();
+      // ---- fold K-half 0 into K-half 1 (rounded fp32 add, RZ-bias compensation), release region 0 -----------
+      const uint32_t taddr = tlane + 256;
+#pragma unroll 1
+      for (int cc = 0; cc < NCH; ++cc) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tlane + cc * 32, v0);
+        tmem_ld32(taddr + cc * 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          v1[c] = __float_as_uint((__uint_as_float(v0[c]) + __uint_as_float(v1[c])) * a.acc_scale);
+        tmem_st32(taddr + cc * 32, v1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[0]);
 
       if (MODE == MODE_DENSE || MODE == MODE_RAW) {
-        float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H;
-        const float* rrow = (MODE == MODE_DENSE && a.epi == 2) ? a.res + (size_t)(row0 + r) * a.ldo + nb * H : nullptr;
+        float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
+        const float* rrow = (MODE == MODE_DENSE && a.epi == 2) ? a.res + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC : nullptr;
+        const float* bias = (MODE == MODE_DENSE && a.b2) ? a.b2 + nb * H + hf * HC : nullptr;
 #pragma unroll 1
-        for (int cc = 0; cc < H / 32; ++cc) {
+        for (int cc = 0; cc < NCH; ++cc) {
           uint32_t v[32];
           tmem_ld32(taddr + cc * 32, v);
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = cc * 32 + c4 * 4 + e;
-                float t = __uint_as_float(v[c4 * 4 + e]) * a.acc_scale;
-                if (MODE == MODE_DENSE) {
-                  if (a.b2) t += __ldg(a.b2 + nb * H + c);
-                  if (a.epi == 1) t = silu(t);
-                }
-                o[e] = t;
+              float o[4] = {__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
+                            __uint_as_float(v[c4 * 4 + 3])};
+              if (bias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + c4 * 4));
+                o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
               }
+              if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
               if (rrow) {
                 const float4 rs = __ldg(reinterpret_cast<const float4*>(rrow + cc * 32 + c4 * 4));
                 o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
@@ -340,59 +409,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[acc]);
+        mbar_arrive(&acc_empty[1]);
       } else {
-        // ---- pass 1: m = SiLU(D + b2), row dot with w_att / w6 ------------------------------------------
+        // ---- pass 1: m = SiLU(D + b2), partial row dot with w_att / w6 over this thread's column half ----------
         float dot = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < H / 32; ++cc) {
+        for (int cc = 0; cc < NCH; ++cc) {
           uint32_t v[32];
           tmem_ld32(taddr + cc * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float m = silu(fmaf(__uint_as_float(v[c]), a.acc_scale, __ldg(a.b2 + cc * 32 + c)));
-            dot = fmaf(__ldg(a.w_out + cc * 32 + c), m, dot);
-            v[c] = __float_as_uint(m);
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b2 + cc * 32 + c4 * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wo + cc * 32 + c4 * 4);
+            const float m0 = silu(__uint_as_float(v[c4 * 4 + 0]) + b4.x);
+            const float m1 = silu(__uint_as_float(v[c4 * 4 + 1]) + b4.y);
+            const float m2 = silu(__uint_as_float(v[c4 * 4 + 2]) + b4.z);
+            const float m3 = silu(__uint_as_float(v[c4 * 4 + 3]) + b4.w);
+            dot = fmaf(w4.x, m0, dot); dot = fmaf(w4.y, m1, dot); dot = fmaf(w4.z, m2, dot); dot = fmaf(w4.w, m3, dot);
+            v[c4 * 4 + 0] = __float_as_uint(m0); v[c4 * 4 + 1] = __float_as_uint(m1);
+            v[c4 * 4 + 2] = __float_as_uint(m2); v[c4 * 4 + 3] = __float_as_uint(m3);
           }
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
         }
+        s_dot[hf * TM + r] = dot;
         if (MODE == MODE_EQUIV) {
           tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);      // accumulator no longer needed
-          float phi = a.use_tanh ? tanhf(dot) : dot;
-          float dx = __fmul_rn(ux, phi), dy = __fmul_rn(uy, phi), dz = __fmul_rn(uz, phi);
-          if (a.use_tanh) { dx = __fmul_rn(dx, a.coords_range); dy = __fmul_rn(dy, a.coords_range); dz = __fmul_rn(dz, a.coords_range); }
-          s_dx[4 * r] = valid ? dx : 0.f; s_dx[4 * r + 1] = valid ? dy : 0.f; s_dx[4 * r + 2] = valid ? dz : 0.f;
-          named_bar_sync(1, 128);
+          mbar_arrive(&acc_empty[1]);      // accumulator no longer needed
+          named_bar_sync(1, EPI_T);        // dot halves + s_i visible
+          if (hf == 0) {
+            const float d = s_dot[r] + s_dot[TM + r];
+            float phi = a.use_tanh ? tanhf(d) : d;
+            float dx = __fmul_rn(ux, phi), dy = __fmul_rn(uy, phi), dz = __fmul_rn(uz, phi);
+            if (a.use_tanh) { dx = __fmul_rn(dx, a.coords_range); dy = __fmul_rn(dy, a.coords_range); dz = __fmul_rn(dz, a.coords_range); }
+            s_dx[4 * r] = valid ? dx : 0.f; s_dx[4 * r + 1] = valid ? dy : 0.f; s_dx[4 * r + 2] = valid ? dz : 0.f;
+          }
+          named_bar_sync(1, EPI_T);
           // segment heads sum their run sequentially (ascending j, like the reference's scatter order)
-          if (valid && (r == 0 || s_i[r - 1] != my_i)) {
+          if (hf == 0 && valid && (r == 0 || s_i[r - 1] != my_i)) {
             float sx = 0.f, sy = 0.f, sz = 0.f;
             for (int q = r; q < nrows && s_i[q] == my_i; ++q) { sx += s_dx[4 * q]; sy += s_dx[4 * q + 1]; sz += s_dx[4 * q + 2]; }
             atomicAdd(a.out + (size_t)my_i * 3, sx);
             atomicAdd(a.out + (size_t)my_i * 3 + 1, sy);
             atomicAdd(a.out + (size_t)my_i * 3 + 2, sz);
           }
-          named_bar_sync(1, 128);             // s_i / s_dx reused by the next tile
+          named_bar_sync(1, EPI_T);           // s_i / s_dx / s_dot reused by the next tile
         } else {
           tmem_st_wait();
-          float g = a.attention ? sigmoidf_(dot + __ldg(a.b_out)) : 1.0f;
+          named_bar_sync(1, EPI_T);           // dot halves + s_i visible
+          float g = a.attention ? sigmoidf_(s_dot[r] + s_dot[TM + r] + __ldg(a.b_out)) : 1.0f;
           if (!valid) g = 0.f;
-          // ---- piece list: maximal runs of equal receiver ---------------------------------------------------
-          named_bar_sync(1, 128);             // s_i visible
-          const bool head = valid && (r == 0 || s_i[r - 1] != my_i);
+          // ---- piece list: maximal runs of equal receiver (built by the hf == 0 warps) ----------------------
+          const bool head = hf == 0 && valid && (r == 0 || s_i[r - 1] != my_i);
           const unsigned bal = __ballot_sync(0xffffffffu, head);
-          if (lane == 0) s_cnt[warp] = __popc(bal);
-          named_bar_sync(1, 128);
+          if (lane == 0 && hf == 0) s_cnt[warp] = __popc(bal);
+          named_bar_sync(1, EPI_T);
           int base = 0, npieces = 0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { const int c = s_cnt[w]; if (w < warp) base += c; npieces += c; }
+          for (int w = 0; w < 4; ++w) { const int c = s_cnt[w]; if (w < (warp & 3)) base += c; npieces += c; }
           if (head) s_ps[base + __popc(bal & ((1u << lane) - 1u))] = r;
-          if (r == 0) s_ps[npieces] = nrows;
-          named_bar_sync(1, 128);
+          if (et == 0) s_ps[npieces] = nrows;
+          named_bar_sync(1, EPI_T);
           // ---- pass 2: e = m * g, transpose 32 columns at a time through smem, per-piece column sums ---------
+          // (the two column halves run independently on named barriers 2 and 3)
 #pragma unroll 1
-          for (int cc = 0; cc < H / 32; ++cc) {
+          for (int cc = 0; cc < NCH; ++cc) {
             uint32_t v[32];
             tmem_ld32(taddr + cc * 32, v);
             tmem_ld_wait();
@@ -402,17 +483,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
                                       __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
               *reinterpret_cast<float4*>(T + r * 32 + ((c4 ^ (r & 7)) << 2)) = e4;
             }
-            named_bar_sync(1, 128);
-            for (int k = warp; k < npieces; k += 4) {
+            named_bar_sync(2 + hf, 128);
+            for (int k = (warp & 3); k < npieces; k += 4) {
               const int q0 = s_ps[k], q1 = s_ps[k + 1];
               float sum = 0.f;
               for (int q = q0; q < q1; ++q) sum += T[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
-              atomicAdd(a.out + (size_t)s_i[q0] * H + cc * 32 + lane, sum);
+              atomicAdd(a.out + (size_t)s_i[q0] * H + hf * HC + cc * 32 + lane, sum);
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(2 + hf, 128);
           }
           tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);
+          mbar_arrive(&acc_empty[1]);
+          named_bar_sync(1, EPI_T);           // s_i / s_ps / s_dot reused by the next tile
         }
       }
     }
@@ -420,19 +502,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (CS > 1) cluster_sync_all();             // no CTA exits while a peer may still multicast into it
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int H, int MODE>
+template <int H, int MODE, int CS>
 int launch_mode(const TcArgs& a, cudaStream_t st) {
   using S = Smem<H>;
   static int sm_count = 0;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_kernel<H, MODE, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
     if (e != cudaSuccess) {
       set_error("tc_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
       return -2;
@@ -442,23 +525,58 @@ int launch_mode(const TcArgs& a, cudaStream_t st) {
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const int work = a.n_tile * a.n_blocks;
-  if (work == 0) return 0;
-  const int grid = work < sm_count ? work : sm_count;
+  GEOLDM_REQUIRE(a.n_slabs % 2 == 0, "tc_kernel: K/32 = %d must be even", a.n_slabs);
+  const int n_tile_pad = (a.n_tile + CS - 1) / CS * CS;
+  const int work = n_tile_pad * a.n_blocks;
+  if (a.n_tile == 0) return 0;
+  int grid = work < sm_count ? work : sm_count;
+  grid = grid / CS * CS;
   TcArgs args = a;
-  args.acc_scale = a.terms == 3 ? 1.0f + RZ_BIAS_PER_MMA * (float)(a.n_slabs * (BK / 8) * 3) : 1.0f;
-  tc_kernel<H, MODE><<<grid, NTHREADS, S::ALLOC, st>>>(args);
-  GEOLDM_CHECK_LAUNCH("tc_kernel");
+  args.acc_scale = a.terms == 3 ? 1.0f + RZ_BIAS_PER_MMA * (float)((a.n_slabs / 2) * (BK / 8) * 3) : 1.0f;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = S::ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<H, MODE, CS>, args);
+  if (e != cudaSuccess) {
+    set_error("tc_kernel launch: %s", cudaGetErrorString(e));
+    return -2;
+  }
   return 0;
+}
+
+int g_cluster = 2;   // W-multicast cluster size (1, 2 or 4); GEOLDM_TC_CLUSTER overrides
+
+template <int H, int MODE>
+int launch_cs(const TcArgs& a, cudaStream_t st) {
+  static bool read_env = false;
+  if (!read_env) {
+    const char* e = getenv("GEOLDM_TC_CLUSTER");
+    if (e) g_cluster = atoi(e);
+    read_env = true;
+  }
+  switch (g_cluster) {
+    case 1: return launch_mode<H, MODE, 1>(a, st);
+    case 4: return launch_mode<H, MODE, 4>(a, st);
+    default: return launch_mode<H, MODE, 2>(a, st);
+  }
 }
 
 template <int MODE>
 int launch_h(int H, const TcArgs& a, cudaStream_t st) {
   switch (H) {
-    case 64: return launch_mode<64, MODE>(a, st);
-    case 128: return launch_mode<128, MODE>(a, st);
-    case 192: return launch_mode<192, MODE>(a, st);
-    case 256: return launch_mode<256, MODE>(a, st);
+    case 64: return launch_cs<64, MODE>(a, st);
+    case 128: return launch_cs<128, MODE>(a, st);
+    case 192: return launch_cs<192, MODE>(a, st);
+    case 256: return launch_cs<256, MODE>(a, st);
     default: set_error("tcgen05 kernels support hidden_nf 64/128/192/256, got %d", H); return -1;
   }
 }

@@ -19,11 +19,12 @@ __global__ void tc_pack_kernel(int H, const float* __restrict__ w, int n_out, in
   const float v = w[idx];
   const float hi = tf32_rne(v);
   const float lo = tf32_rne(v - hi);
-  // float offset inside one H x 32 image, canonical SWIZZLE_128B K-major order
-  const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) | (kl & 3));
-  float* img = pack + ((size_t)(nb * n_slabs + slab) * 2) * (size_t)H * 32;
+  // stage = (slab, N-half): [hi image | lo image], each H/2 rows x 32 floats in canonical SWIZZLE_128B K-major order
+  const int NH = H / 2, half = nl / NH, rl = nl % NH;
+  const int off = (rl >> 3) * 256 + (rl & 7) * 32 + ((((kl >> 2) ^ (rl & 7)) << 2) | (kl & 3));
+  float* img = pack + ((size_t)((nb * n_slabs + slab) * 2 + half) * 2) * (size_t)NH * 32;
   img[off] = hi;
-  img[(size_t)H * 32 + off] = lo;
+  img[(size_t)NH * 32 + off] = lo;
 }
 }  // namespace geoldm
 
@@ -31,7 +32,7 @@ extern "C" {
 size_t geoldm_tc_pack_bytes(int H, int n_out, int k) { return (size_t)n_out * k * 2 * sizeof(float) + 0 * H; }
 
 int geoldm_tc_pack(int H, const float* w, int n_out, int k, void* pack, void* stream) {
-  GEOLDM_REQUIRE(H % 16 == 0 && H <= 256 && n_out % H == 0 && k % 32 == 0, "tc_pack: H=%d n_out=%d k=%d", H, n_out, k);
+  GEOLDM_REQUIRE(H % 32 == 0 && H <= 256 && n_out % H == 0 && k % 64 == 0, "tc_pack: H=%d n_out=%d k=%d", H, n_out, k);
   const size_t tot = (size_t)n_out * k;
   if (tot == 0) return 0;
   geoldm::tc_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
