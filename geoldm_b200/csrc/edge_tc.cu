@@ -39,6 +39,7 @@ constexpr int TM = 128;         // rows per tile (TMEM lanes)
 constexpr int BK = 32;          // k-slab: 32 fp32/tf32 = 128 bytes per row = one swizzle row
 constexpr int NTHREADS = 576;    // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int NWS = 3;          // W pipeline stages
+constexpr int NAS = 3;          // A pipeline stages
 constexpr int EPI_T = 256, PROD_T = 256;
 constexpr int WARP_LOAD = 16, WARP_MMA = 17;
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
@@ -68,6 +69,7 @@ struct TcArgs {
   int ldo; int epi;         // dense: row stride of out/res; 0 none, 1 SiLU, 2 residual
   float norm_constant, coords_range;
   int attention, use_tanh;
+  int debug;                // timing experiments only (GEOLDM_TC_DEBUG): 1 skip W copies, 2 skip A generation, 4 skip tail
   float acc_scale;          // 1 + RZ_BIAS_PER_MMA * (#MMAs accumulated per output): see below
 };
 
@@ -87,15 +89,15 @@ struct Smem {
   static constexpr uint32_t A_STAGE = 2u * TM * 128u;         // hi + lo
   static constexpr uint32_t OFF_W = 0;
   static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
-  static constexpr uint32_t OFF_T = OFF_A + 2 * A_STAGE;      // [2][128][32] fp32 transposition tiles (one per column half)
-  static constexpr uint32_t OFF_SI = OFF_T + 2 * TM * 32 * 4; // int   [128] receiver per row
+  static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;    // [128][32] fp32 transposition tile
+  static constexpr uint32_t OFF_SI = OFF_T + TM * 32 * 4;     // int   [128] receiver per row
   static constexpr uint32_t OFF_PS = OFF_SI + TM * 4;         // int   [129] piece starts
   static constexpr uint32_t OFF_DX = OFF_PS + (TM + 4) * 4;   // float [128][4] equiv deltas
   static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;       // float [2][128] row-dot partials of the two column halves
   static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;   // float [2][H] staged bias / head vectors
   static constexpr uint32_t OFF_CNT = OFF_VEC + 2 * H * 4;    // int   [8]
-  static constexpr uint32_t OFF_BAR = OFF_CNT + 32;           // 2*NWS + 8 mbarriers
-  static constexpr uint32_t OFF_TMEM = OFF_BAR + (2 * NWS + 8) * 8;
+  static constexpr uint32_t OFF_BAR = OFF_CNT + 32;           // 2*NWS + 2*NAS + 4 mbarriers
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + (2 * NWS + 2 * NAS + 4) * 8;
   static constexpr uint32_t BYTES = OFF_TMEM + 16;
   static constexpr uint32_t ALLOC = BYTES + 1024;             // slack for manual 1024-byte alignment
 };
@@ -110,10 +112,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* w_full = bars;                    // [NWS]
   uint64_t* w_empty = bars + NWS;             // [NWS]
-  uint64_t* a_full = bars + 2 * NWS;          // [2]
-  uint64_t* a_empty = bars + 2 * NWS + 2;     // [2]
-  uint64_t* acc_full = bars + 2 * NWS + 4;    // [2]  K-half 0 / 1 of the current tile complete
-  uint64_t* acc_empty = bars + 2 * NWS + 6;   // [2]  TMEM region 0 / 1 drained by the epilogue
+  uint64_t* a_full = bars + 2 * NWS;                  // [NAS]
+  uint64_t* a_empty = bars + 2 * NWS + NAS;           // [NAS]
+  uint64_t* acc_full = bars + 2 * NWS + 2 * NAS;      // [2]  K-half 0 / 1 of the current tile complete
+  uint64_t* acc_empty = bars + 2 * NWS + 2 * NAS + 2; // [2]  TMEM region 0 / 1 drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
 
   const int tid = threadIdx.x;
@@ -132,11 +134,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], CS);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&a_full[s], PROD_T);
+    for (int s = 0; s < NAS; ++s) {
+      mbar_init(&a_full[s], PROD_T / 32);     // one arrive per producer warp
       mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_T);
+      mbar_init(&acc_empty[s], EPI_T / 32);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         for (int s = 0; s < 2 * a.n_slabs; ++s, ++wit) {       // (slab, N-half) stages
           const int st = wit % NWS;
           mbar_wait(&w_empty[st], ((wit / NWS) & 1) ^ 1);       // every CTA of the cluster released the stage
+          if (a.debug & 1) { mbar_arrive(&w_full[st]); continue; }
           mbar_arrive_expect_tx(&w_full[st], S::W_STAGE);
           constexpr uint32_t PART = S::W_STAGE / CS;
           uint8_t* dst = smem + S::OFF_W + st * S::W_STAGE + crank * PART;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     }
   } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ==============================================================
-    const uint32_t idesc = make_idesc_tf32(NH);
+    const uint32_t idesc = (a.debug & 8) ? make_idesc_tf32(H) : make_idesc_tf32(NH);
     uint32_t wit = 0, ait = 0;
     for (int iter = 0; iter < n_iter; ++iter) {
       for (int kh = 0; kh < 2; ++kh) {
@@ -194,8 +199,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kh * 256;
         for (int s = 0; s < half_slabs; ++s, ++ait) {
-          const int ast = ait & 1;
-          mbar_wait(&a_full[ast], (ait >> 1) & 1);
+          const int ast = ait % NAS;
+          mbar_wait(&a_full[ast], (ait / NAS) & 1);
           for (int nh = 0; nh < 2; ++nh, ++wit) {
             const int wst = wit % NWS;
             mbar_wait(&w_full[wst], (wit / NWS) & 1);
@@ -208,6 +213,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               const uint32_t d = d_tmem + nh * NH;
 #pragma unroll
               for (int kk = 0; kk < BK / 8; ++kk) {
+                if ((a.debug & 8) && nh == 1) break;     // timing experiment: one N=H instruction instead of two N=H/2
+                if ((a.debug & 16) && kk > 0) break;      // timing experiment: quarter of the MMAs
                 const uint64_t da_hi = make_smem_desc_sw128(a_hi + kk * 32), da_lo = make_smem_desc_sw128(a_lo + kk * 32);
                 const uint64_t dw_hi = make_smem_desc_sw128(w_hi + kk * 32), dw_lo = make_smem_desc_sw128(w_lo + kk * 32);
                 if (a.terms == 3) {
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
       }
       for (int s = 0; s < a.n_slabs; ++s, ++it) {
-        const int st = it & 1;
+        const int st = it % NAS;
         const int k0 = s * BK;
         float4 v[4];
         float4 q[4];
@@ -290,7 +297,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           wr = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 4 * chunk));
           wd = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 4 * chunk));
         }
-        mbar_wait(&a_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1);
+        if (a.debug & 2) { __syncwarp(); if (lane == 0) mbar_arrive(&a_full[st]); continue; }
         uint8_t* a_hi = smem + S::OFF_A + st * S::A_STAGE;
         uint8_t* a_lo = a_hi + TM * 128;
 #pragma unroll
@@ -325,7 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           *reinterpret_cast<float4*>(a_lo + off) = lo;
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a_full[st]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[st]);
       }
     }
   } else {
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     constexpr int HC = H / 2;               // columns per half
     constexpr int NCH = HC / 32;            // 32-column chunks per half
     const int et = tid;                     // 0..255
-    float* T = reinterpret_cast<float*>(smem + S::OFF_T) + hf * TM * 32;
+    float* T = reinterpret_cast<float*>(smem + S::OFF_T);
     int* s_i = reinterpret_cast<int*>(smem + S::OFF_SI);
     int* s_ps = reinterpret_cast<int*>(smem + S::OFF_PS);
     float* s_dx = reinterpret_cast<float*>(smem + S::OFF_DX);
@@ -364,6 +373,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       mbar_wait(&acc_full[0], ph);
       mbar_wait(&acc_full[1], ph);
       tc_fence_after();
+      if (a.debug & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&acc_empty[0]); mbar_arrive(&acc_empty[1]); }
+        continue;
+      }
       // ---- fold K-half 0 into K-half 1 (rounded fp32 add, RZ-bias compensation), release region 0 -----------
       const uint32_t taddr = tlane + 256;
 #pragma unroll 1
@@ -379,7 +394,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&acc_empty[0]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[0]);
 
       if (MODE == MODE_DENSE || MODE == MODE_RAW) {
         float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
@@ -409,7 +425,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[1]);
       } else {
         // ---- pass 1: m = SiLU(D + b2), partial row dot with w_att / w6 over this thread's column half ----------
         float dot = 0.f;
@@ -435,7 +452,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         s_dot[hf * TM + r] = dot;
         if (MODE == MODE_EQUIV) {
           tc_fence_before();
-          mbar_arrive(&acc_empty[1]);      // accumulator no longer needed
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[1]);   // accumulator no longer needed
           named_bar_sync(1, EPI_T);        // dot halves + s_i visible
           if (hf == 0) {
             const float d = s_dot[r] + s_dot[TM + r];
@@ -470,30 +488,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           if (head) s_ps[base + __popc(bal & ((1u << lane) - 1u))] = r;
           if (et == 0) s_ps[npieces] = nrows;
           named_bar_sync(1, EPI_T);
-          // ---- pass 2: e = m * g, transpose 32 columns at a time through smem, per-piece column sums ---------
-          // (the two column halves run independently on named barriers 2 and 3)
+          // ---- pass 2: e = m * g, transposed 32 columns at a time through one smem tile: the two column halves
+          //      take turns writing it, all 8 warps take the per-piece column sums (lane = column) -----------------
 #pragma unroll 1
           for (int cc = 0; cc < NCH; ++cc) {
             uint32_t v[32];
             tmem_ld32(taddr + cc * 32, v);
             tmem_ld_wait();
+#pragma unroll 1
+            for (int hsel = 0; hsel < 2; ++hsel) {
+              if (hf == hsel) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
-                                      __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
-              *reinterpret_cast<float4*>(T + r * 32 + ((c4 ^ (r & 7)) << 2)) = e4;
+                for (int c4 = 0; c4 < 8; ++c4) {
+                  float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
+                                          __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
+                  *reinterpret_cast<float4*>(T + r * 32 + ((c4 ^ (r & 7)) << 2)) = e4;
+                }
+              }
+              named_bar_sync(1, EPI_T);
+              for (int k = warp; k < npieces; k += 8) {
+                const int q0 = s_ps[k], q1 = s_ps[k + 1];
+                float sum = 0.f;
+                for (int q = q0; q < q1; ++q) sum += T[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
+                atomicAdd(a.out + (size_t)s_i[q0] * H + hsel * HC + cc * 32 + lane, sum);
+              }
+              named_bar_sync(1, EPI_T);
             }
-            named_bar_sync(2 + hf, 128);
-            for (int k = (warp & 3); k < npieces; k += 4) {
-              const int q0 = s_ps[k], q1 = s_ps[k + 1];
-              float sum = 0.f;
-              for (int q = q0; q < q1; ++q) sum += T[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
-              atomicAdd(a.out + (size_t)s_i[q0] * H + hf * HC + cc * 32 + lane, sum);
-            }
-            named_bar_sync(2 + hf, 128);
           }
           tc_fence_before();
-          mbar_arrive(&acc_empty[1]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[1]);
           named_bar_sync(1, EPI_T);           // s_i / s_ps / s_dot reused by the next tile
         }
       }
@@ -532,6 +556,9 @@ int launch_mode(const TcArgs& a, cudaStream_t st) {
   int grid = work < sm_count ? work : sm_count;
   grid = grid / CS * CS;
   TcArgs args = a;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("GEOLDM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  args.debug = dbg;
   args.acc_scale = a.terms == 3 ? 1.0f + RZ_BIAS_PER_MMA * (float)((a.n_slabs / 2) * (BK / 8) * 3) : 1.0f;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
