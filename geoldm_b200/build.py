@@ -30,7 +30,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build libgeoldm_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = ["-DGEOLDM_TC_PROFILE"] if os.environ.get("GEOLDM_TC_PROFILE") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(proc.stderr)

@@ -31,7 +31,18 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+// cycle-counter instrumentation of the MMA / producer threads: compiled in only with -DGEOLDM_TC_PROFILE
+// (GEOLDM_TC_PROFILE=1 python -m geoldm_b200.build --force; read with scripts/tc_stats.py, GEOLDM_TC_DEBUG=32)
+#ifdef GEOLDM_TC_PROFILE
+#define TC_PROF(...) __VA_ARGS__
+#else
+#define TC_PROF(...)
+#endif
+
 namespace geoldm {
+// cycle counters of the MMA-issuing thread (debug bit 32): where does the tensor pipe's feeder wait?
+__device__ unsigned long long g_tc_stats[8];
+__device__ unsigned long long g_tc_prod[2];
 namespace {
 using namespace tc;
 
@@ -81,6 +92,7 @@ struct TcArgs {
 // FFMA — which removes the bias and leaves only the zero-mean part (6e-7 relative at n = 96).
 constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;
 
+
 template <int H>
 struct Smem {
   static constexpr uint32_t NH = H / 2;                       // W rows (= output columns) per stage
@@ -96,14 +108,15 @@ struct Smem {
   static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;       // float [2][128] row-dot partials of the two column halves
   static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;   // float [2][H] staged bias / head vectors
   static constexpr uint32_t OFF_CNT = OFF_VEC + 2 * H * 4;    // int   [8]
-  static constexpr uint32_t OFF_BAR = OFF_CNT + 32;           // 2*NWS + 2*NAS + 4 mbarriers
-  static constexpr uint32_t OFF_TMEM = OFF_BAR + (2 * NWS + 2 * NAS + 4) * 8;
+  static constexpr uint32_t OFF_BAR = OFF_CNT + 32;           // 3*NWS + 2*NAS + 4 mbarriers
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + (3 * NWS + 2 * NAS + 4) * 8;
   static constexpr uint32_t BYTES = OFF_TMEM + 16;
   static constexpr uint32_t ALLOC = BYTES + 1024;             // slack for manual 1024-byte alignment
 };
 
-template <int H, int MODE, int CS>
+template <int H, int MODE, int CS, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
+  static_assert(!PAIR || CS == 2, "cta_group::2 needs a cluster of exactly two CTAs");
   using S = Smem<H>;
   constexpr int NH = H / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -116,6 +129,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   uint64_t* a_empty = bars + 2 * NWS + NAS;           // [NAS]
   uint64_t* acc_full = bars + 2 * NWS + 2 * NAS;      // [2]  K-half 0 / 1 of the current tile complete
   uint64_t* acc_empty = bars + 2 * NWS + 2 * NAS + 2; // [2]  TMEM region 0 / 1 drained by the epilogue
+  uint64_t* w_peer = bars + 2 * NWS + 2 * NAS + 4;    // [NWS] PAIR: the peer CTA's half of the W stage has landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
 
   const int tid = threadIdx.x;
@@ -125,26 +139,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   // work items: (tile, column block); padded so that all CTAs of a cluster run the same number of iterations on
   // the same column block (they share the W stream); padding tiles have zero rows
   const int n_tile_pad = (a.n_tile + CS - 1) / CS * CS;
-  const int total_work = n_tile_pad * a.n_blocks;
-  const int n_iter = (total_work + (int)gridDim.x - 1) / (int)gridDim.x;
+  // PAIR: a work item is a super-tile of 256 rows (one 128-row tile per CTA of the pair)
+  const int work_per_block = PAIR ? n_tile_pad / 2 : n_tile_pad;
+  const int n_workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int worker = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int total_work = work_per_block * a.n_blocks;
+  const int n_iter = (total_work + n_workers - 1) / n_workers;
   const int half_slabs = a.n_slabs / 2;
 
   if (tid == 0) {
     for (int s = 0; s < NWS; ++s) {
       mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], CS);
+      mbar_init(&w_empty[s], PAIR ? 1 : CS);
+      mbar_init(&w_peer[s], 1);
     }
     for (int s = 0; s < NAS; ++s) {
-      mbar_init(&a_full[s], PROD_T / 32);     // one arrive per producer warp
+      mbar_init(&a_full[s], (PAIR ? 2 : 1) * PROD_T / 32);     // one arrive per producer warp (of both CTAs)
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_T / 32);   // one arrive per epilogue warp
+      mbar_init(&acc_empty[s], (PAIR ? 2 : 1) * EPI_T / 32);   // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == WARP_MMA) tmem_alloc(tmem_slot, 512);
+  if (warp == WARP_MMA) { if (PAIR) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   if (MODE == MODE_GCL || MODE == MODE_EQUIV) {     // stage the per-column vectors of the fused tail
     float* vec = reinterpret_cast<float*>(smem + S::OFF_VEC);
     for (int c = tid; c < H; c += NTHREADS) { vec[c] = a.b2[c]; vec[H + c] = a.w_out[c]; }
@@ -156,9 +175,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   auto tile_of = [&](int iter, int& tile, int& nb, int& row0, int& nrows) {
-    const int work = iter * (int)gridDim.x + (int)blockIdx.x;
-    nb = work / n_tile_pad;
-    tile = work % n_tile_pad;
+    const int work = iter * n_workers + worker;
+    nb = work / work_per_block;
+    tile = PAIR ? 2 * (work % work_per_block) + (int)crank : work % work_per_block;
     if (nb >= a.n_blocks || tile >= a.n_tile) {   // padding
       nb = nb >= a.n_blocks ? a.n_blocks - 1 : nb;
       row0 = 0; nrows = 0;
@@ -170,7 +189,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 
   if (warp == WARP_LOAD) {
     // =========================== W-stage loader (TMA engine, multicast) ===================================
-    if (lane == 0) {
+    if (PAIR) {
+      // each CTA of the pair fetches ITS N-half of every k-slab (the hardware reads B rows [0,H/2) from the leader's
+      // shared memory and [H/2,H) from the peer's); a second lane of the peer forwards "landed" to the leader
+      if (lane == 0) {
+        uint32_t wit = 0;
+        for (int iter = 0; iter < n_iter; ++iter) {
+          int tile, nb, row0, nrows;
+          tile_of(iter, tile, nb, row0, nrows);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_pack) + (size_t)nb * a.n_slabs * 2 * S::W_STAGE;
+          for (int s = 0; s < a.n_slabs; ++s, ++wit) {
+            const int st = wit % NWS;
+            mbar_wait(&w_empty[st], ((wit / NWS) & 1) ^ 1);
+            if (a.debug & 1) { mbar_arrive(&w_full[st]); continue; }
+            mbar_arrive_expect_tx(&w_full[st], S::W_STAGE);
+            bulk_g2s(smem + S::OFF_W + st * S::W_STAGE, src + (size_t)(2 * s + crank) * S::W_STAGE, S::W_STAGE,
+                     &w_full[st]);
+          }
+        }
+      } else if (lane == 1 && crank == 1) {
+        uint32_t wit = 0;
+        for (int iter = 0; iter < n_iter; ++iter)
+          for (int s = 0; s < a.n_slabs; ++s, ++wit) {
+            const int st = wit % NWS;
+            mbar_wait(&w_full[st], (wit / NWS) & 1);
+            mbar_arrive_remote(&w_peer[st], 0);
+          }
+      }
+    } else if (lane == 0) {
       uint32_t wit = 0;
       for (int iter = 0; iter < n_iter; ++iter) {
         int tile, nb, row0, nrows;
@@ -191,6 +237,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     }
   } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ==============================================================
+    if (PAIR) {
+      // leader CTA only: M = 256 (128 rows from each CTA), N = H, operands and accumulators in both CTAs
+      if (crank == 0) {
+        const uint32_t idesc2 = make_idesc_tf32_m256(H);
+        uint32_t wit = 0, ait = 0;
+        TC_PROF(long long t_acc = 0; long long t_a = 0; long long t_w = 0; const long long t_begin = clock64();)
+        for (int iter = 0; iter < n_iter; ++iter) {
+          for (int kh = 0; kh < 2; ++kh) {
+            TC_PROF(long long t0 = clock64();)
+            mbar_wait_cluster(&acc_empty[kh], (iter & 1) ^ 1);
+            TC_PROF(t_acc += clock64() - t0;)
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + kh * 256;
+            for (int s = 0; s < half_slabs; ++s, ++ait, ++wit) {
+              const int ast = ait % NAS, wst = wit % NWS;
+              TC_PROF(t0 = clock64();)
+              mbar_wait_cluster(&a_full[ast], (ait / NAS) & 1);
+              TC_PROF(long long t1 = clock64();)
+              mbar_wait(&w_full[wst], (wit / NWS) & 1);
+              mbar_wait_cluster(&w_peer[wst], (wit / NWS) & 1);
+              TC_PROF(long long t2 = clock64(); t_a += t1 - t0; t_w += t2 - t1;)
+              tc_fence_after();
+              if (lane == 0) {
+                const uint32_t a_hi = smem_u32(smem + S::OFF_A + ast * S::A_STAGE);
+                const uint32_t a_lo = a_hi + TM * 128;
+                const uint32_t w_hi = smem_u32(smem + S::OFF_W + wst * S::W_STAGE);
+                const uint32_t w_lo = w_hi + S::W_IMG;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                  const uint64_t da_hi = make_smem_desc_sw128(a_hi + kk * 32), da_lo = make_smem_desc_sw128(a_lo + kk * 32);
+                  const uint64_t dw_hi = make_smem_desc_sw128(w_hi + kk * 32), dw_lo = make_smem_desc_sw128(w_lo + kk * 32);
+                  if (a.terms == 3) {
+                    mma_tf32_pair(d_tmem, da_lo, dw_hi, idesc2, (s | kk) != 0);
+                    mma_tf32_pair(d_tmem, da_hi, dw_lo, idesc2, 1);
+                    mma_tf32_pair(d_tmem, da_hi, dw_hi, idesc2, 1);
+                  } else {
+                    mma_tf32_pair(d_tmem, da_hi, dw_hi, idesc2, (s | kk) != 0);
+                  }
+                }
+                mma_commit_pair(&w_empty[wst], cmask);
+                mma_commit_pair(&a_empty[ast], cmask);
+                if (s == half_slabs - 1) mma_commit_pair(&acc_full[kh], cmask);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        TC_PROF(if ((a.debug & 32) && lane == 0 && blockIdx.x == 0) {
+          g_tc_stats[0] += (unsigned long long)(clock64() - t_begin);
+          g_tc_stats[1] += (unsigned long long)t_acc;
+          g_tc_stats[2] += (unsigned long long)t_a;
+          g_tc_stats[3] += (unsigned long long)t_w;
+          g_tc_stats[4] += 1ull;
+          g_tc_stats[5] += (unsigned long long)n_iter;
+        })
+      }
+    } else {
     const uint32_t idesc = (a.debug & 8) ? make_idesc_tf32(H) : make_idesc_tf32(NH);
     uint32_t wit = 0, ait = 0;
     for (int iter = 0; iter < n_iter; ++iter) {
@@ -237,13 +340,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
       }
     }
+    }
   } else if (warp >= 8) {
     // =========================== A producers (256 threads) ==============================================
     const int pt = tid - EPI_T;
     const int chunk = pt & 7;        // 16-byte chunk: k = 4*chunk .. 4*chunk+3 inside the slab
     const int rbase = pt >> 3;       // rows rbase + 32 p
     uint32_t it = 0;
+    TC_PROF(long long tp_wait = 0; long long tp_comp = 0; long long tp_fence = 0; long long tp_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
+      TC_PROF(const long long tm0 = clock64();)
       int tile, nb, row0, nrows;
       tile_of(iter, tile, nb, row0, nrows);
       const float* pP[4];
@@ -272,11 +378,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
       }
+      TC_PROF(tp_meta += clock64() - tm0;)
       for (int s = 0; s < a.n_slabs; ++s, ++it) {
         const int st = it % NAS;
         const int k0 = s * BK;
         float4 v[4];
         float4 q[4];
+        TC_PROF(const long long tp0 = clock64();)
         // issue the global loads first; they are in flight while we wait for the stage to drain
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -298,7 +406,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           wd = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 4 * chunk));
         }
         mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1);
-        if (a.debug & 2) { __syncwarp(); if (lane == 0) mbar_arrive(&a_full[st]); continue; }
+        TC_PROF(const long long tp1 = clock64();)
+        if (a.debug & 2) {
+          __syncwarp();
+          if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+          continue;
+        }
         uint8_t* a_hi = smem + S::OFF_A + st * S::A_STAGE;
         uint8_t* a_lo = a_hi + TM * 128;
 #pragma unroll
@@ -332,11 +445,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           *reinterpret_cast<float4*>(a_hi + off) = hi;
           *reinterpret_cast<float4*>(a_lo + off) = lo;
         }
+        TC_PROF(const long long tp2 = clock64();)
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[st]);
+        if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+        TC_PROF(if ((a.debug & 32) && tid == EPI_T && blockIdx.x == 0) {
+          const long long tp3 = clock64();
+          tp_wait += tp1 - tp0; tp_comp += tp2 - tp1; tp_fence += tp3 - tp2;
+        })
       }
     }
+    TC_PROF(if ((a.debug & 32) && tid == EPI_T && blockIdx.x == 0) {
+      atomicAdd(&g_tc_stats[6], (unsigned long long)tp_wait);
+      atomicAdd(&g_tc_stats[7], (unsigned long long)tp_comp);
+      g_tc_prod[0] += (unsigned long long)tp_fence;
+      g_tc_prod[1] += (unsigned long long)tp_meta;
+    })
   } else {
     // ============= epilogue (warps 0-7: thread = (TMEM lane = row, column half)) ==========================
     const int r = (warp & 3) * 32 + lane;   // row / TMEM lane; a warp may only touch lanes 32*(warp%4)..+31
@@ -353,6 +477,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     const float* s_wo = s_b2 + H;
     int* s_cnt = reinterpret_cast<int*>(smem + S::OFF_CNT);
     const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * HC;
+    auto release_acc = [&](int region) {     // one arrive per warp, on the MMA-issuing (leader) CTA's barrier
+      __syncwarp();
+      if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(&acc_empty[region], 0); else mbar_arrive(&acc_empty[region]); }
+    };
     for (int iter = 0; iter < n_iter; ++iter) {
       int tile, nb, row0, nrows;
       tile_of(iter, tile, nb, row0, nrows);
@@ -375,8 +503,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       tc_fence_after();
       if (a.debug & 4) {
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&acc_empty[0]); mbar_arrive(&acc_empty[1]); }
+        release_acc(0);
+        release_acc(1);
         continue;
       }
       // ---- fold K-half 0 into K-half 1 (rounded fp32 add, RZ-bias compensation), release region 0 -----------
@@ -394,8 +522,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       }
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[0]);
+      release_acc(0);
 
       if (MODE == MODE_DENSE || MODE == MODE_RAW) {
         float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
@@ -425,8 +552,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[1]);
+        release_acc(1);
       } else {
         // ---- pass 1: m = SiLU(D + b2), partial row dot with w_att / w6 over this thread's column half ----------
         float dot = 0.f;
@@ -452,8 +578,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         s_dot[hf * TM + r] = dot;
         if (MODE == MODE_EQUIV) {
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[1]);   // accumulator no longer needed
+          release_acc(1);                  // accumulator no longer needed
           named_bar_sync(1, EPI_T);        // dot halves + s_i visible
           if (hf == 0) {
             const float d = s_dot[r] + s_dot[TM + r];
@@ -508,16 +633,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               named_bar_sync(1, EPI_T);
               for (int k = warp; k < npieces; k += 8) {
                 const int q0 = s_ps[k], q1 = s_ps[k + 1];
-                float sum = 0.f;
-                for (int q = q0; q < q1; ++q) sum += T[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
-                atomicAdd(a.out + (size_t)s_i[q0] * H + hsel * HC + cc * 32 + lane, sum);
+                // four interleaved partial sums hide the shared-memory latency of the row walk
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int q = q0;
+                for (; q + 4 <= q1; q += 4) {
+                  s0 += T[(q + 0) * 32 + ((((lane >> 2) ^ ((q + 0) & 7)) << 2) | (lane & 3))];
+                  s1 += T[(q + 1) * 32 + ((((lane >> 2) ^ ((q + 1) & 7)) << 2) | (lane & 3))];
+                  s2 += T[(q + 2) * 32 + ((((lane >> 2) ^ ((q + 2) & 7)) << 2) | (lane & 3))];
+                  s3 += T[(q + 3) * 32 + ((((lane >> 2) ^ ((q + 3) & 7)) << 2) | (lane & 3))];
+                }
+                for (; q < q1; ++q) s0 += T[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
+                atomicAdd(a.out + (size_t)s_i[q0] * H + hsel * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
               }
               named_bar_sync(1, EPI_T);
             }
           }
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[1]);
+          release_acc(1);
           named_bar_sync(1, EPI_T);           // s_i / s_ps / s_dot reused by the next tile
         }
       }
@@ -529,17 +661,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   if (CS > 1) cluster_sync_all();             // no CTA exits while a peer may still multicast into it
   if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int H, int MODE, int CS>
+template <int H, int MODE, int CS, bool PAIR>
 int launch_mode(const TcArgs& a, cudaStream_t st) {
   using S = Smem<H>;
   static int sm_count = 0;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_kernel<H, MODE, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_kernel<H, MODE, CS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
     if (e != cudaSuccess) {
       set_error("tc_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
       return -2;
@@ -551,7 +683,7 @@ int launch_mode(const TcArgs& a, cudaStream_t st) {
   }
   GEOLDM_REQUIRE(a.n_slabs % 2 == 0, "tc_kernel: K/32 = %d must be even", a.n_slabs);
   const int n_tile_pad = (a.n_tile + CS - 1) / CS * CS;
-  const int work = n_tile_pad * a.n_blocks;
+  const int work = n_tile_pad * a.n_blocks;     // in 128-row tiles (a PAIR work item covers two of them)
   if (a.n_tile == 0) return 0;
   int grid = work < sm_count ? work : sm_count;
   grid = grid / CS * CS;
@@ -572,7 +704,7 @@ int launch_mode(const TcArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<H, MODE, CS>, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_kernel<H, MODE, CS, PAIR>, args);
   if (e != cudaSuccess) {
     set_error("tc_kernel launch: %s", cudaGetErrorString(e));
     return -2;
@@ -581,6 +713,7 @@ int launch_mode(const TcArgs& a, cudaStream_t st) {
 }
 
 int g_cluster = 2;   // W-multicast cluster size (1, 2 or 4); GEOLDM_TC_CLUSTER overrides
+int g_pair = 1;      // 1: cta_group::2 MMAs over a CTA pair (default); GEOLDM_TC_PAIR=0 selects cta_group::1
 
 template <int H, int MODE>
 int launch_cs(const TcArgs& a, cudaStream_t st) {
@@ -588,12 +721,15 @@ int launch_cs(const TcArgs& a, cudaStream_t st) {
   if (!read_env) {
     const char* e = getenv("GEOLDM_TC_CLUSTER");
     if (e) g_cluster = atoi(e);
+    e = getenv("GEOLDM_TC_PAIR");
+    if (e) g_pair = atoi(e);
     read_env = true;
   }
+  if (g_pair) return launch_mode<H, MODE, 2, true>(a, st);
   switch (g_cluster) {
-    case 1: return launch_mode<H, MODE, 1>(a, st);
-    case 4: return launch_mode<H, MODE, 4>(a, st);
-    default: return launch_mode<H, MODE, 2>(a, st);
+    case 1: return launch_mode<H, MODE, 1, false>(a, st);
+    case 4: return launch_mode<H, MODE, 4, false>(a, st);
+    default: return launch_mode<H, MODE, 2, false>(a, st);
   }
 }
 
@@ -653,3 +789,13 @@ int launch_tc_selftest(int H, int terms, const float* pq, const int* edge_i, con
 }  // namespace geoldm
 
 extern "C" int geoldm_has_tcgen05(void) { return 1; }
+// debug: read and reset the MMA-thread cycle counters {total, wait acc_empty, wait a_full, wait w_full, launches, tiles}
+extern "C" int geoldm_tc_read_stats(unsigned long long* host_out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_out, geoldm::g_tc_stats, sizeof(unsigned long long) * 8);
+  cudaMemcpyFromSymbol(host_out + 8, geoldm::g_tc_prod, sizeof(unsigned long long) * 2);
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(geoldm::g_tc_stats, zero, sizeof(zero));
+  cudaMemcpyToSymbol(geoldm::g_tc_prod, zero, sizeof(unsigned long long) * 2);
+  return 0;
+}

@@ -173,6 +173,9 @@ int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2,
  * of 2H floats (the P|Q layout), rows split into tiles by tile_row like the edge kernels */
 int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, const int* tile_row, int n_tile,
                        int n_rows, const void* w_pack, float* out, void* stream);
+/* debug (GEOLDM_TC_DEBUG & 32): read+reset cycle counters of the MMA-issuing thread of CTA 0:
+ * {total, wait acc_empty, wait a_full, wait w_full, launches, tiles, 0, 0}; synchronises the device */
+int geoldm_tc_read_stats(unsigned long long* host_out);
 /* Philox4x32-10 standard normals (Box-Muller), the sampler's noise stream exposed for tests:
  * out[4*d+e] = e-th normal of block counter=(d, node, blk, seed>>32), key=(mol_id, (uint32)seed), i.e. what
  * geoldm_sampler_update draws for draw index d, node `node` of molecule `mol_id`, columns 4*blk+e. */
