@@ -404,6 +404,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
           wr = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 4 * chunk));
           wd = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 4 * chunk));
+          // pull the next k-slab of the same P / Q rows into L1 (a tile touches ~40 distinct node rows = ~5 KB per
+          // slab): costs no registers, and next iteration's loads no longer pay the L2 round trip
+          if (s + 1 < a.n_slabs) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+              if (valid[p]) { prefetch_l1(pP[p] + k0 + BK); prefetch_l1(pQ[p] + k0 + BK); }
+          }
         }
         mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1);
         TC_PROF(const long long tp1 = clock64();)
