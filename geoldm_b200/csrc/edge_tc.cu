@@ -50,7 +50,7 @@ constexpr int TM = 128;         // rows per tile (TMEM lanes)
 constexpr int BK = 32;          // k-slab: 32 fp32/tf32 = 128 bytes per row = one swizzle row
 constexpr int NTHREADS = 576;    // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int NWS = 3;          // W pipeline stages
-constexpr int NAS = 3;          // A pipeline stages
+constexpr int NAS = 2;          // A pipeline stages
 constexpr int EPI_T = 256, PROD_T = 256;
 constexpr int WARP_LOAD = 16, WARP_MMA = 17;
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
@@ -101,10 +101,10 @@ struct Smem {
   static constexpr uint32_t A_STAGE = 2u * TM * 128u;         // hi + lo
   static constexpr uint32_t OFF_W = 0;
   static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
-  static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;    // [128][32] fp32 transposition tile
-  static constexpr uint32_t OFF_SI = OFF_T + TM * 32 * 4;     // int   [128] receiver per row
+  static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;    // 8 warp-private [32][32] fp32 transposition tiles
+  static constexpr uint32_t OFF_SI = OFF_T + 8 * 32 * 32 * 4; // int   [128] receiver per row
   static constexpr uint32_t OFF_PS = OFF_SI + TM * 4;         // int   [129] piece starts
-  static constexpr uint32_t OFF_DX = OFF_PS + (TM + 4) * 4;   // float [128][4] equiv deltas
+  static constexpr uint32_t OFF_DX = OFF_PS + 8 * 34 * 4;     // float [128][4] equiv deltas   (PS: 8 warps x 34 ints)
   static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;       // float [2][128] row-dot partials of the two column halves
   static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;   // float [2][H] staged bias / head vectors
   static constexpr uint32_t OFF_CNT = OFF_VEC + 2 * H * 4;    // int   [8]
@@ -582,82 +582,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
         }
+        // the two warps that share this lane quarter (column halves) exchange their partial dots: 64-thread barrier
         s_dot[hf * TM + r] = dot;
+        if (MODE == MODE_GCL) tmem_st_wait();
+        named_bar_sync(2 + (warp & 3), 64);
+        const float full_dot = s_dot[r] + s_dot[TM + r];
+        // receiver runs ("pieces") inside this warp's 32 rows; a receiver's rows span at most two warps when n-1 <= 32,
+        // so every (receiver, column) gets at most two partial atomics: order-independent, hence deterministic
+        const int prev_i = __shfl_up_sync(0xffffffffu, my_i, 1);
+        const bool head = valid && (lane == 0 || prev_i != my_i);
+        const unsigned hm = __ballot_sync(0xffffffffu, head);
+        const int nval = __popc(__ballot_sync(0xffffffffu, valid));
+        const int npiece = __popc(hm);
         if (MODE == MODE_EQUIV) {
           tc_fence_before();
           release_acc(1);                  // accumulator no longer needed
-          named_bar_sync(1, EPI_T);        // dot halves + s_i visible
           if (hf == 0) {
-            const float d = s_dot[r] + s_dot[TM + r];
-            float phi = a.use_tanh ? tanhf(d) : d;
+            float phi = a.use_tanh ? tanhf(full_dot) : full_dot;
             float dx = __fmul_rn(ux, phi), dy = __fmul_rn(uy, phi), dz = __fmul_rn(uz, phi);
             if (a.use_tanh) { dx = __fmul_rn(dx, a.coords_range); dy = __fmul_rn(dy, a.coords_range); dz = __fmul_rn(dz, a.coords_range); }
             s_dx[4 * r] = valid ? dx : 0.f; s_dx[4 * r + 1] = valid ? dy : 0.f; s_dx[4 * r + 2] = valid ? dz : 0.f;
+            __syncwarp();
+            // run heads sum their rows sequentially (ascending j, like the reference's scatter order)
+            if (head) {
+              const unsigned after = hm & ~((2u << lane) - 1u);           // heads strictly above this lane
+              const int q1 = after ? (__ffs(after) - 1) : nval;
+              float sx = 0.f, sy = 0.f, sz = 0.f;
+              for (int q = lane; q < q1; ++q) {
+                const float* d = s_dx + 4 * ((warp & 3) * 32 + q);
+                sx += d[0]; sy += d[1]; sz += d[2];
+              }
+              atomicAdd(a.out + (size_t)my_i * 3, sx);
+              atomicAdd(a.out + (size_t)my_i * 3 + 1, sy);
+              atomicAdd(a.out + (size_t)my_i * 3 + 2, sz);
+            }
+            __syncwarp();                  // s_dx rows reused by the next tile
           }
-          named_bar_sync(1, EPI_T);
-          // segment heads sum their run sequentially (ascending j, like the reference's scatter order)
-          if (hf == 0 && valid && (r == 0 || s_i[r - 1] != my_i)) {
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            for (int q = r; q < nrows && s_i[q] == my_i; ++q) { sx += s_dx[4 * q]; sy += s_dx[4 * q + 1]; sz += s_dx[4 * q + 2]; }
-            atomicAdd(a.out + (size_t)my_i * 3, sx);
-            atomicAdd(a.out + (size_t)my_i * 3 + 1, sy);
-            atomicAdd(a.out + (size_t)my_i * 3 + 2, sz);
-          }
-          named_bar_sync(1, EPI_T);           // s_i / s_dx / s_dot reused by the next tile
+          named_bar_sync(2 + (warp & 3), 64);   // s_dot reused by the next tile
         } else {
-          tmem_st_wait();
-          named_bar_sync(1, EPI_T);           // dot halves + s_i visible
-          float g = a.attention ? sigmoidf_(s_dot[r] + s_dot[TM + r] + __ldg(a.b_out)) : 1.0f;
+          float g = a.attention ? sigmoidf_(full_dot + __ldg(a.b_out)) : 1.0f;
           if (!valid) g = 0.f;
-          // ---- piece list: maximal runs of equal receiver (built by the hf == 0 warps) ----------------------
-          const bool head = hf == 0 && valid && (r == 0 || s_i[r - 1] != my_i);
-          const unsigned bal = __ballot_sync(0xffffffffu, head);
-          if (lane == 0 && hf == 0) s_cnt[warp] = __popc(bal);
-          named_bar_sync(1, EPI_T);
-          int base = 0, npieces = 0;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) { const int c = s_cnt[w]; if (w < (warp & 3)) base += c; npieces += c; }
-          if (head) s_ps[base + __popc(bal & ((1u << lane) - 1u))] = r;
-          if (et == 0) s_ps[npieces] = nrows;
-          named_bar_sync(1, EPI_T);
-          // ---- pass 2: e = m * g, transposed 32 columns at a time through one smem tile: the two column halves
-          //      take turns writing it, all 8 warps take the per-piece column sums (lane = column) -----------------
+          // ---- pass 2: e = m * g; each warp transposes its own 32 rows x 16 columns through a private 2 KB smem
+          //      slice (no CTA barriers) and its two half-warps take the column sums of alternate pieces ------------
+          float* Tw = reinterpret_cast<float*>(smem + S::OFF_T) + warp * (32 * 32);
+          int* psw = s_ps + warp * 34;        // this warp's piece starts (+ end sentinel)
+          if (head) psw[__popc(hm & ((1u << lane) - 1u))] = lane;
+          if (lane == 0) psw[npiece] = nval;
+          __syncwarp();
 #pragma unroll 1
           for (int cc = 0; cc < NCH; ++cc) {
             uint32_t v[32];
             tmem_ld32(taddr + cc * 32, v);
             tmem_ld_wait();
-#pragma unroll 1
-            for (int hsel = 0; hsel < 2; ++hsel) {
-              if (hf == hsel) {
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                  float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
-                                          __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
-                  *reinterpret_cast<float4*>(T + r * 32 + ((c4 ^ (r & 7)) << 2)) = e4;
-                }
-              }
-              named_bar_sync(1, EPI_T);
-              for (int k = warp; k < npieces; k += 8) {
-                const int q0 = s_ps[k], q1 = s_ps[k + 1];
-                // four interleaved partial sums hide the shared-memory latency of the row walk
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                int q = q0;
-                for (; q + 4 <= q1; q += 4) {
-                  s0 += T[(q + 0) * 32 + ((((lane >> 2) ^ ((q + 0) & 7)) << 2) | (lane & 3))];
-                  s1 += T[(q + 1) * 32 + ((((lane >> 2) ^ ((q + 1) & 7)) << 2) | (lane & 3))];
-                  s2 += T[(q + 2) * 32 + ((((lane >> 2) ^ ((q + 2) & 7)) << 2) | (lane & 3))];
-                  s3 += T[(q + 3) * 32 + ((((lane >> 2) ^ ((q + 3) & 7)) << 2) | (lane & 3))];
-                }
-                for (; q < q1; ++q) s0 += T[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
-                atomicAdd(a.out + (size_t)s_i[q0] * H + hsel * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
-              }
-              named_bar_sync(1, EPI_T);
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
+                                      __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
+              *reinterpret_cast<float4*>(Tw + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = e4;
             }
+            __syncwarp();
+            for (int pc = 0; pc < npiece; ++pc) {        // lane = column; pieces in row order
+              const int q0 = psw[pc], q1 = psw[pc + 1];
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              int q = q0;
+              for (; q + 4 <= q1; q += 4) {
+                s0 += Tw[(q + 0) * 32 + ((((lane >> 2) ^ ((q + 0) & 7)) << 2) | (lane & 3))];
+                s1 += Tw[(q + 1) * 32 + ((((lane >> 2) ^ ((q + 1) & 7)) << 2) | (lane & 3))];
+                s2 += Tw[(q + 2) * 32 + ((((lane >> 2) ^ ((q + 2) & 7)) << 2) | (lane & 3))];
+                s3 += Tw[(q + 3) * 32 + ((((lane >> 2) ^ ((q + 3) & 7)) << 2) | (lane & 3))];
+              }
+              for (; q < q1; ++q) s0 += Tw[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
+              const int pi = s_i[(warp & 3) * 32 + q0];   // written by this quarter's hf == 0 warp before the 64-thread barrier
+              atomicAdd(a.out + (size_t)pi * H + hf * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
+            }
+            __syncwarp();
           }
           tc_fence_before();
           release_acc(1);
-          named_bar_sync(1, EPI_T);           // s_i / s_ps / s_dot reused by the next tile
+          named_bar_sync(2 + (warp & 3), 64);   // s_dot reused by the next tile
         }
       }
     }
