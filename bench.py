@@ -366,8 +366,12 @@ def main():
                    "kind": "port", "sec_per_step": sec,
                    "sample": f"median of 5 oracle sample_p_zs_given_zt steps on the first {CPU_SAMPLE_MOLS} workload "
                              f"molecules (padded to 29, fp32, torch CPU), extrapolated x{FORWARDS_PER_MOLECULE}"}
-        S = margs.inv_sublayers
-        launches_per_step = 1 + margs.n_layers * (S * 4 + 3) + 1 + 1 + 3 + 1 + 1   # embed, blocks, outproj, prep, finish, upd, adv
+        S, Lb = margs.inv_sublayers, margs.n_layers
+        if mode == "fp32":      # every GCL / equiv has its own projection launch
+            egnn_launches = 1 + Lb * (S * 4 + 3) + 1
+        else:                   # equiv P|Q fused with the next block's gcl_0 P|Q
+            egnn_launches = 1 + 1 + Lb * (S * 3 + (S - 1) + 3) + 1
+        launches_per_step = egnn_launches + 1 + 1 + 2 + 1 + 1   # + prep, nan-flag fill, finish a/b, update, advance
         line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if mode == "fp32" else mode, "data": "synthetic", "config": workload_config(n_gpus),

@@ -33,7 +33,7 @@ class Gcl(C.Structure):
 
 
 class Block(C.Structure):
-    _fields_ = [("gcl", Gcl * MAX_SUBLAYERS), ("equiv", EdgeMlp)]
+    _fields_ = [("gcl", Gcl * MAX_SUBLAYERS), ("equiv", EdgeMlp), ("tc_pack_pq4", fp), ("pq4_b", fp)]
 
 
 class EgnnWeights(C.Structure):

@@ -28,16 +28,19 @@ static Workspace carve(void* base, int n_node, int H) {
     return p;
   };
   const size_t nh = (size_t)n_node * H;
-  w.h = take(nh); w.h2 = take(nh); w.t1 = take(nh); w.agg = take(nh); w.pq = take(2 * nh);
+  w.h = take(nh); w.h2 = take(nh); w.t1 = take(nh); w.agg = take(nh); w.pq = take(4 * nh);
   w.xa = take((size_t)3 * n_node); w.xb = take((size_t)3 * n_node); w.xagg = take((size_t)3 * n_node); w.dx = take((size_t)3 * n_node);
   w.bytes = off;
   return w;
 }
 
 static int edge_dispatch(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
-                         const float* pq, const float* x, const float* x0, float* out, cudaStream_t st) {
-  if (cfg.mma_mode == GEOLDM_MMA_FP32_SIMT) return launch_edge_simt(cfg, w, b, equiv, pq, x, x0, out, st);
-  return launch_edge_tc(cfg, w, b, equiv, pq, x, x0, out, st);
+                         const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
+  if (cfg.mma_mode == GEOLDM_MMA_FP32_SIMT) {
+    GEOLDM_REQUIRE(pq_ld == 2 * cfg.hidden_nf, "edge_simt expects a [N][2H] projection buffer");
+    return launch_edge_simt(cfg, w, b, equiv, pq, x, x0, out, st);
+  }
+  return launch_edge_tc(cfg, w, b, equiv, pq, pq_ld, x, x0, out, st);
 }
 }  // namespace geoldm
 
@@ -82,17 +85,25 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   float* x_bufs[2] = {ws.xa, ws.xb};
   int xi = 0;
   float *h = ws.h, *h2 = ws.h2;
+  // P|Q of the upcoming gcl_0: [N][pq_ld] at pq_next; produced either stand-alone or by the previous block's fused
+  // 4-column-block projection (equiv P|Q in columns [0,2H), next gcl_0 P|Q in [2H,4H))
+  const float* pq_next = nullptr;
+  int pq_next_ld = 2 * H;
   for (int l = 0; l < cfg->n_layers; ++l) {
     const geoldm_block& blk = w->block[l];
     for (int s = 0; s < cfg->inv_sublayers; ++s) {
       const geoldm_gcl& g = blk.gcl[s];
-      if (tcore) {
+      const float* pq = ws.pq;
+      int pq_ld = 2 * H;
+      if (s == 0 && pq_next) {
+        pq = pq_next; pq_ld = pq_next_ld;
+      } else if (tcore) {
         if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, g.edge.tc_pack_pq, 2, g.edge.pq_b, nullptr, 0, ws.pq, N, st))) return rc;
       } else {
         if ((rc = launch_linear(h, H, nullptr, 0, 1.f, g.edge.pq_wt, g.edge.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
       }
       cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
-      if ((rc = edge_dispatch(*cfg, g.edge, *b, false, ws.pq, x_cur, x_in, ws.agg, st))) return rc;
+      if ((rc = edge_dispatch(*cfg, g.edge, *b, false, pq, pq_ld, x_cur, x_in, ws.agg, st))) return rc;
       if (tcore) {
         if ((rc = launch_linear_tc(H, terms, h, H, ws.agg, H, cfg->agg_div, g.tc_pack_node1, 1, g.node_b1, nullptr, 1, ws.t1, N, st))) return rc;
         if ((rc = launch_linear_tc(H, terms, ws.t1, H, nullptr, 0, 1.f, g.tc_pack_node2, 1, g.node_b2, h, 2, h2, N, st))) return rc;
@@ -103,13 +114,20 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
       float* tmp = h; h = h2; h2 = tmp;
     }
     const geoldm_edge_mlp& e = blk.equiv;
-    if (tcore) {
+    int pq_ld = 2 * H;
+    pq_next = nullptr;
+    if (tcore && blk.tc_pack_pq4 && l + 1 < cfg->n_layers) {
+      if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, blk.tc_pack_pq4, 4, blk.pq4_b, nullptr, 0, ws.pq, N, st))) return rc;
+      pq_ld = 4 * H;
+      pq_next = ws.pq + 2 * H;
+      pq_next_ld = 4 * H;
+    } else if (tcore) {
       if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, e.tc_pack_pq, 2, e.pq_b, nullptr, 0, ws.pq, N, st))) return rc;
     } else {
       if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
     }
     cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
-    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, x_cur, x_in, ws.xagg, st))) return rc;
+    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, pq_ld, x_cur, x_in, ws.xagg, st))) return rc;
     const bool last = (l + 1 == cfg->n_layers);
     float* x_next = last ? x_out : x_bufs[xi];
     float* dx_next = (last && dx_out) ? dx_out : ws.dx;   // dx is updated in place (elementwise)
@@ -126,12 +144,12 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
 int geoldm_edge_gcl(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b, const float* pq,
                     const float* x, const float* x0, float* agg, void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
-  return edge_dispatch(*cfg, *w, *b, false, pq, x, x0, agg, (cudaStream_t)stream);
+  return edge_dispatch(*cfg, *w, *b, false, pq, 2 * cfg->hidden_nf, x, x0, agg, (cudaStream_t)stream);
 }
 int geoldm_edge_equiv(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b, const float* pq,
                       const float* x, const float* x0, float* xagg, void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
-  return edge_dispatch(*cfg, *w, *b, true, pq, x, x0, xagg, (cudaStream_t)stream);
+  return edge_dispatch(*cfg, *w, *b, true, pq, 2 * cfg->hidden_nf, x, x0, xagg, (cudaStream_t)stream);
 }
 int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt, const float* bias,
                   const float* res, int epi, float* out, int m, int n, int mma_mode, void* stream) {

@@ -76,7 +76,7 @@ __device__ __forceinline__ EdgeGeom edge_geom(const float* __restrict__ x, const
 int launch_edge_simt(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                      const float* pq, const float* x, const float* x0, float* out, cudaStream_t st);
 int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
-                   const float* pq, const float* x, const float* x0, float* out, cudaStream_t st);
+                   const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st);
 int launch_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt,
                   const float* bias, const float* res, int epi, float* out, int m, int n, cudaStream_t st);
 

@@ -50,7 +50,6 @@ constexpr int TM = 128;         // rows per tile (TMEM lanes)
 constexpr int BK = 32;          // k-slab: 32 fp32/tf32 = 128 bytes per row = one swizzle row
 constexpr int NTHREADS = 576;    // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int NWS = 3;          // W pipeline stages
-constexpr int NAS = 2;          // A pipeline stages
 constexpr int EPI_T = 256, PROD_T = 256;
 constexpr int WARP_LOAD = 16, WARP_MMA = 17;
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
@@ -64,7 +63,8 @@ struct TcArgs {
   int n_slabs;              // K / 32
   int terms;                // 3 (3xTF32) or 1 (single TF32 pass)
   // A operand sources
-  const float* pq;          // [N][2H]              (edge modes, RAW)
+  const float* pq;          // [N][pq_ld] P in columns [0,H), Q in [H,2H)   (edge modes, RAW)
+  int pq_ld;
   const float* x; const float* x0;
   const int* edge_i; const int* edge_j;
   const float* w_rd;        // [2][H]
@@ -93,8 +93,10 @@ struct TcArgs {
 constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;
 
 
-template <int H>
+template <int H, int MODE>
 struct Smem {
+  static constexpr int NAS = (MODE == 0) ? 2 : 3;              // A pipeline stages (GCL spends 32 KB on transposition tiles)
+  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 32 * 4 : 0u;
   static constexpr uint32_t NH = H / 2;                       // W rows (= output columns) per stage
   static constexpr uint32_t W_IMG = NH * 128u;                // one tf32 image of a stage
   static constexpr uint32_t W_STAGE = 2u * W_IMG;             // hi + lo
@@ -102,7 +104,7 @@ struct Smem {
   static constexpr uint32_t OFF_W = 0;
   static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
   static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;    // 8 warp-private [32][32] fp32 transposition tiles
-  static constexpr uint32_t OFF_SI = OFF_T + 8 * 32 * 32 * 4; // int   [128] receiver per row
+  static constexpr uint32_t OFF_SI = OFF_T + T_BYTES;         // int   [128] receiver per row
   static constexpr uint32_t OFF_PS = OFF_SI + TM * 4;         // int   [129] piece starts
   static constexpr uint32_t OFF_DX = OFF_PS + 8 * 34 * 4;     // float [128][4] equiv deltas   (PS: 8 warps x 34 ints)
   static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;       // float [2][128] row-dot partials of the two column halves
@@ -117,7 +119,8 @@ struct Smem {
 template <int H, int MODE, int CS, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   static_assert(!PAIR || CS == 2, "cta_group::2 needs a cluster of exactly two CTAs");
-  using S = Smem<H>;
+  using S = Smem<H, MODE>;
+  constexpr int NAS = S::NAS;
   constexpr int NH = H / 2;
   extern __shared__ uint8_t smem_raw[];
   // same offset in every CTA of the cluster (multicast writes and barrier arrives address peers by offset)
@@ -367,10 +370,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             pQ[p] = a.a2 ? a.a2 + (size_t)(row0 + r) * a.k2 + 4 * chunk : nullptr;
           } else {
             const int i = a.edge_i[row0 + r];
-            pP[p] = a.pq + (size_t)i * (2 * H) + 4 * chunk;
+            pP[p] = a.pq + (size_t)i * a.pq_ld + 4 * chunk;
             if (MODE != MODE_RAW) {
               const int j = a.edge_j[row0 + r];
-              pQ[p] = a.pq + (size_t)j * (2 * H) + H + 4 * chunk;
+              pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 4 * chunk;
               EdgeGeom g = edge_geom(a.x, a.x0, i, j, a.norm_constant);
               rr[p] = g.r;
               dd[p] = g.d0;
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 
 template <int H, int MODE, int CS, bool PAIR>
 int launch_mode(const TcArgs& a, cudaStream_t st) {
-  using S = Smem<H>;
+  using S = Smem<H, MODE>;
   static int sm_count = 0;
   static bool configured = false;
   if (!configured) {
@@ -755,7 +758,7 @@ int launch_h(int H, const TcArgs& a, cudaStream_t st) {
 }  // namespace
 
 int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
-                   const float* pq, const float* x, const float* x0, float* out, cudaStream_t st) {
+                   const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
   GEOLDM_REQUIRE(b.tile_m == TM, "edge_tc: batch tile_m=%d, kernel needs %d", b.tile_m, TM);
   GEOLDM_REQUIRE(w.tc_pack != nullptr, "edge_tc: tc_pack missing (weights not packed for the tensor-core path)");
   GEOLDM_REQUIRE(equiv || !cfg.attention || w.b_out != nullptr, "edge_tc: attention needs b_out");
@@ -763,7 +766,7 @@ int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, cons
   a.n_tile = b.n_tile; a.n_rows = b.n_edge; a.tile_row = b.tile_row; a.n_blocks = 1;
   a.n_slabs = cfg.hidden_nf / BK;
   a.terms = cfg.mma_mode == GEOLDM_MMA_TF32 ? 1 : 3;
-  a.pq = pq; a.x = x; a.x0 = x0; a.edge_i = b.edge_i; a.edge_j = b.edge_j; a.w_rd = w.w_rd;
+  a.pq = pq; a.pq_ld = pq_ld; a.x = x; a.x0 = x0; a.edge_i = b.edge_i; a.edge_j = b.edge_j; a.w_rd = w.w_rd;
   a.w_pack = reinterpret_cast<const float*>(w.tc_pack);
   a.b2 = w.b2; a.w_out = w.w_out; a.b_out = w.b_out; a.out = out;
   a.norm_constant = cfg.norm_constant; a.coords_range = cfg.coords_range;
@@ -791,7 +794,7 @@ int launch_tc_selftest(int H, int terms, const float* pq, const int* edge_i, con
                        int n_rows, const void* w_pack, float* out, cudaStream_t st) {
   TcArgs a{};
   a.n_tile = n_tile; a.n_rows = n_rows; a.tile_row = tile_row; a.n_blocks = 1; a.n_slabs = H / BK; a.terms = terms;
-  a.pq = pq; a.edge_i = edge_i; a.w_pack = reinterpret_cast<const float*>(w_pack); a.out = out; a.ldo = H;
+  a.pq = pq; a.pq_ld = 2 * H; a.edge_i = edge_i; a.w_pack = reinterpret_cast<const float*>(w_pack); a.out = out; a.ldo = H;
   return launch_h<MODE_RAW>(H, a, st);
 }
 

@@ -196,6 +196,13 @@ class EGNN(nn.Module):
                 cg.tc_pack_node2 = tc_pack(g.node_mlp[2].weight)
             q = blk.gcl_equiv
             w.block[b].equiv = edge(q.coord_mlp[0], q.coord_mlp[2], q.coord_mlp[4], None)
+            w.block[b].tc_pack_pq4, w.block[b].pq4_b = None, None
+            if tcore and b + 1 < self.n_layers:
+                nxt = getattr(getattr(self, f"e_block_{b + 1}"), "gcl_0").edge_mlp[0]
+                we, wn = q.coord_mlp[0].weight, nxt.weight
+                w.block[b].tc_pack_pq4 = tc_pack(torch.cat([we[:, :H], we[:, H:2 * H], wn[:, :H], wn[:, H:2 * H]], dim=0))
+                zb = torch.zeros_like(nxt.bias)
+                w.block[b].pq4_b = dev(torch.cat([q.coord_mlp[0].bias, zb, nxt.bias, zb]))
         self._pack, self._pack_key = (w, keep), key
         return self._pack
 

@@ -80,6 +80,10 @@ typedef struct {
 typedef struct {
   geoldm_gcl gcl[GEOLDM_MAX_SUBLAYERS];
   geoldm_edge_mlp equiv;
+  /* tensor-core path: this block's coord_mlp P|Q and the NEXT block's gcl_0 P|Q read the same h, so they are one
+   * GEMM with 4 column blocks: rows [equiv src; equiv dst; next gcl_0 src; next gcl_0 dst] (NULL in the last block) */
+  const void* tc_pack_pq4;
+  const float* pq4_b;        /* [4H] = [equiv b1 | 0 | next gcl_0 b1 | 0] */
 } geoldm_block;
 
 typedef struct {
