@@ -96,7 +96,7 @@ constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;
 template <int H, int MODE>
 struct Smem {
   static constexpr int NAS = (MODE == 0) ? 2 : 3;              // A pipeline stages (GCL spends 32 KB on transposition tiles)
-  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 32 * 4 : 0u;
+  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 36 * 4 : 0u;   // 8 warps x [32 rows][36 floats]
   static constexpr uint32_t NH = H / 2;                       // W rows (= output columns) per stage
   static constexpr uint32_t W_IMG = NH * 128u;                // one tf32 image of a stage
   static constexpr uint32_t W_STAGE = 2u * W_IMG;             // hi + lo
@@ -627,7 +627,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           if (!valid) g = 0.f;
           // ---- pass 2: e = m * g; each warp transposes its own 32 rows x 16 columns through a private 2 KB smem
           //      slice (no CTA barriers) and its two half-warps take the column sums of alternate pieces ------------
-          float* Tw = reinterpret_cast<float*>(smem + S::OFF_T) + warp * (32 * 32);
+          // row stride 36 floats: 16-byte aligned rows whose float4 stores (lane = row) and column reads (lane = column)
+          // are both bank-conflict free without an XOR swizzle
+          float* Tw = reinterpret_cast<float*>(smem + S::OFF_T) + warp * (32 * 36);
           int* psw = s_ps + warp * 34;        // this warp's piece starts (+ end sentinel)
           if (head) psw[__popc(hm & ((1u << lane) - 1u))] = lane;
           if (lane == 0) psw[npiece] = nval;
@@ -641,20 +643,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int c4 = 0; c4 < 8; ++c4) {
               float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
                                       __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
-              *reinterpret_cast<float4*>(Tw + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = e4;
+              *reinterpret_cast<float4*>(Tw + lane * 36 + c4 * 4) = e4;
             }
             __syncwarp();
             for (int pc = 0; pc < npiece; ++pc) {        // lane = column; pieces in row order
               const int q0 = psw[pc], q1 = psw[pc + 1];
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              const float* tp = Tw + q0 * 36 + lane;
               int q = q0;
-              for (; q + 4 <= q1; q += 4) {
-                s0 += Tw[(q + 0) * 32 + ((((lane >> 2) ^ ((q + 0) & 7)) << 2) | (lane & 3))];
-                s1 += Tw[(q + 1) * 32 + ((((lane >> 2) ^ ((q + 1) & 7)) << 2) | (lane & 3))];
-                s2 += Tw[(q + 2) * 32 + ((((lane >> 2) ^ ((q + 2) & 7)) << 2) | (lane & 3))];
-                s3 += Tw[(q + 3) * 32 + ((((lane >> 2) ^ ((q + 3) & 7)) << 2) | (lane & 3))];
+              for (; q + 4 <= q1; q += 4, tp += 4 * 36) {
+                s0 += tp[0];
+                s1 += tp[36];
+                s2 += tp[72];
+                s3 += tp[108];
               }
-              for (; q < q1; ++q) s0 += Tw[q * 32 + ((((lane >> 2) ^ (q & 7)) << 2) | (lane & 3))];
+              for (; q < q1; ++q, tp += 36) s0 += tp[0];
               const int pi = s_i[(warp & 3) * 32 + q0];   // written by this quarter's hf == 0 warp before the 64-thread barrier
               atomicAdd(a.out + (size_t)pi * H + hf * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
             }
