@@ -374,9 +374,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             if (MODE != MODE_RAW) {
               const int j = a.edge_j[row0 + r];
               pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 4 * chunk;
-              EdgeGeom g = edge_geom(a.x, a.x0, i, j, a.norm_constant);
-              rr[p] = g.r;
-              dd[p] = g.d0;
+              // squared distances only (the unit vector is needed by the EQUIV epilogue, not here);
+              // same association as edge_geom / torch.sum(d**2, 1)
+              const float* xi = a.x + 3 * (size_t)i;
+              const float* xj = a.x + 3 * (size_t)j;
+              const float* yi = a.x0 + 3 * (size_t)i;
+              const float* yj = a.x0 + 3 * (size_t)j;
+              const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+              const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
+              rr[p] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+              dd[p] = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
             }
           }
         }
