@@ -20,6 +20,7 @@ from torch import nn
 from . import _lib
 from .egnn import EGNN
 from .packing import RaggedBatch, pack_from_masks
+from .train import wrapper_forward_train
 
 
 class _MaskCache:
@@ -100,6 +101,13 @@ class _EgnnWrapper(nn.Module):
             self._bufs = b
         return b
 
+    def _wants_grad(self, xh, context):
+        """Autograd path (train.py) when a gradient can be asked for: grad mode on and either the module is in
+        train() mode or an input requires grad.  eval() + plain inputs -> the fused inference kernels."""
+        if not torch.is_grad_enabled():
+            return False
+        return self.training or xh.requires_grad or (context is not None and context.requires_grad)
+
     def _check_inputs(self, xh, node_mask):
         if not xh.is_cuda:
             raise _lib.GeoldmError("geoldm_b200 has no CPU path: inputs must be CUDA tensors")
@@ -134,9 +142,14 @@ class EGNN_dynamics_QM9(_EgnnWrapper):
         self.register_buffer("nan_flag", torch.zeros(1, dtype=torch.int32), persistent=False)
         self.to(device)
 
-    @torch.no_grad()
     def _forward(self, t, xh, node_mask, edge_mask, context):
         self._check_inputs(xh, node_mask)
+        if self._wants_grad(xh, context):
+            return wrapper_forward_train(self, t, xh, node_mask, edge_mask, context, True)
+        with torch.no_grad():
+            return self._forward_infer(t, xh, node_mask, edge_mask, context)
+
+    def _forward_infer(self, t, xh, node_mask, edge_mask, context):
         bs, n_nodes, dims = xh.shape
         batch = self._masks.get(node_mask.view(bs, n_nodes, 1), edge_mask, self.validate_masks)
         h_dims = dims - self.n_dims
@@ -186,9 +199,14 @@ class EGNN_decoder_QM9(_EgnnWrapper):
         self.register_buffer("nan_flag", torch.zeros(1, dtype=torch.int32), persistent=False)
         self.to(device)
 
-    @torch.no_grad()
     def _forward(self, xh, node_mask, edge_mask, context):
         self._check_inputs(xh, node_mask)
+        if self._wants_grad(xh, context):
+            return wrapper_forward_train(self, None, xh, node_mask, edge_mask, context, False)
+        with torch.no_grad():
+            return self._forward_infer(xh, node_mask, edge_mask, context)
+
+    def _forward_infer(self, xh, node_mask, edge_mask, context):
         bs, n_nodes, dims = xh.shape
         batch = self._masks.get(node_mask.view(bs, n_nodes, 1), edge_mask, self.validate_masks)
         xh_flat = xh.reshape(bs * n_nodes, dims).contiguous()

@@ -1,0 +1,159 @@
+"""Training-side (autograd) path of the EGNN wrappers — SURVEY §8 configs 2 and 5.
+
+Correctness-first companion of the fused inference kernels: the network is evaluated on the same ragged packing, every
+``nn.Linear`` with GEMM-sized dimensions runs on this repo's fp32 CUDA kernels in all three directions
+(forward ``geoldm_linear``, input gradient ``geoldm_linear`` with the untransposed weight, weight gradient
+``geoldm_gemm_tn``) through ``torch.autograd.Function``; gathers, segment sums (``index_add_``) and element-wise maths are
+library ops recorded by autograd.  It shares the ``nn.Parameter`` objects of the inference modules, so optimisers, EMA and
+``DistributedDataParallel`` (NCCL gradient all-reduce) work unchanged.  A fused recompute-in-kernel backward on the
+tensor cores is round-2 work.
+
+Reference: egnn/egnn_new.py:30-65,86-105,134-147,184-197; egnn/models.py:49-113,335-381.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .packing import RaggedBatch
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the geoldm_b200 GEMM kernels (fp32 FFMA), x [M,K], W [N,K] (PyTorch layout)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        wt = weight.t().contiguous()                      # k-major [K][N]
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().geoldm_linear(_lib.ptr(x), K, None, 0, 1.0, _lib.ptr(wt), _lib.ptr(bias), None, 0,
+                                            _lib.ptr(out), M, N, 0, _stream(x)), "geoldm_linear(fwd)")
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        L = _lib.lib()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            w = weight.contiguous()                       # [N][K] is already k-major for dX = dY W
+            dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
+            _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
+                                       _stream(x)), "geoldm_linear(dX)")
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(N, K, device=x.device, dtype=torch.float32)
+            _lib.check(L.geoldm_gemm_tn(_lib.ptr(dy), N, _lib.ptr(x), K, _lib.ptr(dw), K, M, N, K, _stream(x)),
+                       "geoldm_gemm_tn(dW)")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """nn.Linear forward/backward on our kernels when the shapes are GEMM-sized, library fallback for the tiny heads
+    (embedding in/out, attention and coordinate heads: K or N < 16)."""
+    K, N = weight.shape[1], weight.shape[0]
+    if x.is_cuda and K % 16 == 0 and N % 16 == 0 and x.dtype == torch.float32:
+        return _LinearFn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+def _coord2diff(x, ei, ej, norm_constant):
+    d = x.index_select(0, ei) - x.index_select(0, ej)
+    r = (d * d).sum(1, keepdim=True)
+    return r, d / (torch.sqrt(r + 1e-8) + norm_constant)
+
+
+def _edge_mlp(h, first, second, ei, ej, r, d0, H):
+    """Split first layer (per-node projections + two distance columns) and second layer, both + SiLU."""
+    w1 = first.weight
+    wpq = torch.cat([w1[:, :H], w1[:, H:2 * H]], dim=0)                     # [2H, H]
+    bpq = torch.cat([first.bias, torch.zeros_like(first.bias)])
+    pq = linear(h, wpq, bpq)
+    pre1 = pq[:, :H].index_select(0, ei) + pq[:, H:].index_select(0, ej) + r * w1[:, 2 * H] + d0 * w1[:, 2 * H + 1]
+    return F.silu(linear(F.silu(pre1), second.weight, second.bias))
+
+
+def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
+    """EGNN.forward with autograd on ragged tensors: h [N, in_nf], x [N, 3] -> (h [N, out_nf], x [N, 3])."""
+    H = egnn.hidden_nf
+    ei, ej = batch.edge_i.long(), batch.edge_j.long()
+    N = batch.n_node
+    if egnn.aggregation_method == "mean":
+        if batch.n_max <= 0:
+            raise ValueError("aggregation_method='mean' needs the padded n_max (egnn_new.py:269-273)")
+        div = float(batch.n_max)
+    else:
+        div = float(egnn.normalization_factor)
+    d0, _ = _coord2diff(x, ei, ej, 1.0)
+    h = F.linear(h, egnn.embedding.weight, egnn.embedding.bias)
+    for b in range(egnn.n_layers):
+        blk = getattr(egnn, f"e_block_{b}")
+        r, u = _coord2diff(x, ei, ej, float(egnn.norm_constant))
+        for s in range(egnn.inv_sublayers):
+            g = getattr(blk, f"gcl_{s}")
+            m = _edge_mlp(h, g.edge_mlp[0], g.edge_mlp[2], ei, ej, r, d0, H)
+            if egnn.attention:
+                m = m * torch.sigmoid(F.linear(m, g.att_mlp[0].weight, g.att_mlp[0].bias))
+            agg = torch.zeros(N, H, device=h.device, dtype=h.dtype).index_add_(0, ei, m) / div
+            t1 = F.silu(linear(torch.cat([h, agg], dim=1), g.node_mlp[0].weight, g.node_mlp[0].bias))
+            h = h + linear(t1, g.node_mlp[2].weight, g.node_mlp[2].bias)
+        q = blk.gcl_equiv
+        m2 = _edge_mlp(h, q.coord_mlp[0], q.coord_mlp[2], ei, ej, r, d0, H)
+        sc = F.linear(m2, q.coord_mlp[4].weight)
+        trans = u * torch.tanh(sc) * egnn.coords_range if egnn.tanh else u * sc
+        x = x + torch.zeros(N, 3, device=x.device, dtype=x.dtype).index_add_(0, ei, trans) / div
+    h = F.linear(h, egnn.embedding_out.weight, egnn.embedding_out.bias)
+    return h, x
+
+
+def _remove_mean_ragged(v, batch: RaggedBatch):
+    mol = batch.node_mol.long()
+    cnt = torch.as_tensor(batch.n_nodes, device=v.device, dtype=v.dtype).unsqueeze(1)
+    mean = torch.zeros(batch.n_mol, v.shape[1], device=v.device, dtype=v.dtype).index_add_(0, mol, v) / cnt
+    return v - mean.index_select(0, mol)
+
+
+def wrapper_forward_train(wrapper, t, xh, node_mask, edge_mask, context, is_dynamics: bool):
+    """EGNN_dynamics_QM9._forward / EGNN_decoder_QM9._forward with autograd (padded in, padded out)."""
+    bs, n_nodes, dims = xh.shape
+    batch = wrapper._masks.get(node_mask.view(bs, n_nodes, 1), edge_mask, wrapper.validate_masks)
+    src = batch.node_src.long()
+    flat = xh.reshape(bs * n_nodes, dims).index_select(0, src)
+    x = flat[:, :wrapper.n_dims]
+    h = flat[:, wrapper.n_dims:]
+    if is_dynamics and wrapper.condition_time:
+        t = torch.as_tensor(t, dtype=xh.dtype, device=xh.device)
+        t_mol = t.reshape(1).expand(bs) if t.numel() == 1 else t.reshape(bs)
+        h = torch.cat([h, t_mol.index_select(0, batch.node_mol.long()).unsqueeze(1)], dim=1)
+    if context is not None:
+        h = torch.cat([h, context.reshape(bs * n_nodes, -1).index_select(0, src)], dim=1)
+    h_f, x_f = egnn_forward_train(wrapper.egnn, h, x, batch)
+    if is_dynamics:
+        vel = x_f - x
+        keep = wrapper.egnn.out_node_nf - wrapper.context_node_nf - int(wrapper.condition_time)
+        h_f = h_f[:, :keep]
+    else:
+        vel = x_f
+    vel = torch.where(torch.isnan(vel).any(), torch.zeros_like(vel), vel)      # batch-wide NaN guard (models.py:100-102)
+    vel = _remove_mean_ragged(vel, batch)
+    out_r = torch.cat([vel, h_f], dim=1)
+    out = torch.zeros(bs * n_nodes, out_r.shape[1], device=xh.device, dtype=xh.dtype).index_copy(0, src, out_r)
+    out = out.view(bs, n_nodes, -1)
+    if is_dynamics:
+        return out
+    return out[:, :, :wrapper.n_dims], out[:, :, wrapper.n_dims:]

@@ -177,6 +177,10 @@ int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2,
  * of 2H floats (the P|Q layout), rows split into tiles by tile_row like the edge kernels */
 int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, const int* tile_row, int n_tile,
                        int n_rows, const void* w_pack, float* out, void* stream);
+/* ---- training side: weight-gradient GEMM  C[n][k] += A[m][n]^T * B[m][k]  (fp32 FFMA, caller
+ * zeroes C; lda/ldb multiples of 4).  Forward and input-gradient GEMMs of a Linear layer use geoldm_linear. */
+int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
+                   void* stream);
 /* debug (GEOLDM_TC_DEBUG & 32): read+reset cycle counters of the MMA-issuing thread of CTA 0:
  * {total, wait acc_empty, wait a_full, wait w_full, launches, tiles, 0, 0}; synchronises the device */
 int geoldm_tc_read_stats(unsigned long long* host_out);
