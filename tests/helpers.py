@@ -16,7 +16,7 @@ def load_golden(name):
     c = meta["cfg"]
     c["normalize_factors"] = tuple(c["normalize_factors"])
     cfg = O.OracleConfig(**c)
-    arrays = {k: torch.from_numpy(f[k]) for k in f.files if k != "meta"}
+    arrays = {k: (f[k] if f[k].dtype.kind in "US" else torch.from_numpy(f[k])) for k in f.files if k != "meta"}
     sd = O.make_state_dict(cfg, meta["seed"], meta["tamed"])
     return cfg, sd, arrays, meta
 
