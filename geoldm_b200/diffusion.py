@@ -9,7 +9,7 @@ that a reference ``state_dict`` (``buffer``, ``gamma.gamma``, ``dynamics.egnn.*`
 every step is  prep -> EGNN kernels -> velocity/CoM -> z_s = mu + sigma*eps  with the step index and
 per-step scalars in device memory, captured once as a CUDA graph and replayed T times; there is no host
 synchronisation inside the loop (the reference does >= 10 per step).
-Training-side methods (``forward``/``compute_loss``) are outside this path.
+The training objective (``forward``) lives in losses.py and runs the denoiser/decoder through train.py's autograd path.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _lib
+from . import _lib, losses
 from .dynamics import EGNN_decoder_QM9, EGNN_dynamics_QM9, EGNN_encoder_QM9, _stream
 from .packing import RaggedBatch, pack_from_masks
 
@@ -64,6 +64,27 @@ class EnHierarchicalVAE(nn.Module):
         self.kl_weight = kl_weight
         self.norm_values, self.norm_biases = norm_values, norm_biases
         self.register_buffer('buffer', torch.zeros(1))
+
+    def encode(self, x, h, node_mask=None, edge_mask=None, context=None):
+        """q(z|x): encoder means and the fixed 0.0032 standard deviations (en_diffusion.py:1001-1015)."""
+        xh = torch.cat([x, h['categorical'].to(x.dtype), h['integer'].to(x.dtype)], dim=2)
+        z_x_mu, _, z_h_mu, _ = self.encoder._forward(xh, node_mask, edge_mask, context)
+        bs = z_x_mu.shape[0]
+        sigma_x = torch.full((bs, 1, 1), 0.0032, device=x.device, dtype=z_x_mu.dtype)
+        sigma_h = torch.full((bs, 1, self.latent_node_nf), 0.0032, device=x.device, dtype=z_h_mu.dtype)
+        return z_x_mu, sigma_x, z_h_mu, sigma_h
+
+    def compute_reconstruction_error(self, xh_rec, xh):
+        return losses.reconstruction_error(self, xh_rec, xh)
+
+    def compute_loss(self, x, h, node_mask, edge_mask, context, *, draws=None):
+        return losses.vae_loss(self, x, h, node_mask, edge_mask, context, draws=draws)
+
+    def forward(self, x, h, node_mask=None, edge_mask=None, context=None, *, draws=None):
+        """First-stage objective (en_diffusion.py:928-937)."""
+        bs, n = x.shape[0], x.shape[1]
+        edge_mask = None if edge_mask is None else edge_mask.reshape(bs * n * n, 1)
+        return self.compute_loss(x, h, node_mask.reshape(bs, n, 1), edge_mask, context, draws=draws)[0]
 
     @torch.no_grad()
     def decode(self, z_xh, node_mask=None, edge_mask=None, context=None):
@@ -294,6 +315,16 @@ class EnLatentDiffusion(nn.Module):
         out[src] = out_r
         return out.view(bs, n, D)
 
-    def forward(self, x, h, node_mask=None, edge_mask=None, context=None):
-        raise NotImplementedError("the training loss (EnLatentDiffusion.forward, en_diffusion.py:1136-1191) is "
-                                  "outside the sampling hot path (SURVEY §8f rank 1)")
+    def train(self, mode: bool = True):
+        """A frozen first stage stays in eval() whatever the outer mode is (en_diffusion.py:1234-1239)."""
+        super().train(mode)
+        if not self.trainable_ae:
+            self.vae.eval()
+        return self
+
+    def forward(self, x, h, node_mask=None, edge_mask=None, context=None, *, draws=None):
+        """Per-molecule training loss (train(): l2) or NLL estimate (eval()), en_diffusion.py:1136-1191.
+        ``draws`` (keyword-only, not in the reference) injects the random draws for parity tests."""
+        bs, n = x.shape[0], x.shape[1]
+        edge_mask = None if edge_mask is None else edge_mask.reshape(bs * n * n, 1)
+        return losses.latent_diffusion_nll(self, x, h, node_mask.reshape(bs, n, 1), edge_mask, context, draws=draws)

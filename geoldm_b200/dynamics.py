@@ -20,7 +20,7 @@ from torch import nn
 from . import _lib
 from .egnn import EGNN
 from .packing import RaggedBatch, pack_from_masks
-from .train import wrapper_forward_train
+from .train import linear as train_linear, wrapper_forward_train
 
 
 class _MaskCache:
@@ -220,15 +220,20 @@ class EGNN_decoder_QM9(_EgnnWrapper):
         return out[:, :, :self.n_dims], out[:, :, self.n_dims:]
 
 
-class EGNN_encoder_QM9(nn.Module):
-    """Parameter container only (egnn/models.py:137-175) so that reference checkpoints load with
-    strict=True.  The encoder is used in training only — not on the sampling path."""
+class EGNN_encoder_QM9(_EgnnWrapper):
+    """egnn/models.py:137-263: one-block EGNN (out = hidden_nf) + final_mlp -> (x mean, x std, h mean, h std).
+    Inside EnLatentDiffusion the encoder is always evaluated without grad (its output is detached,
+    en_diffusion.py:1155) and runs on the fused inference kernels; with grad (first-stage training) it goes through
+    train.py like the other wrappers."""
 
     def __init__(self, in_node_nf, context_node_nf, out_node_nf, n_dims, hidden_nf=64, device='cpu',
                  act_fn=torch.nn.SiLU(), n_layers=4, attention=False, tanh=False, mode='egnn_dynamics',
                  norm_constant=0, inv_sublayers=2, sin_embedding=False, normalization_factor=100,
-                 aggregation_method='sum', include_charges=True, mma_mode="fp32"):
+                 aggregation_method='sum', include_charges=True, mma_mode="fp32", validate_masks=True):
         super().__init__()
+        if mode != 'egnn_dynamics':
+            raise NotImplementedError("only mode='egnn_dynamics' is supported")
+        self.mode = mode
         self.egnn = EGNN(in_node_nf=in_node_nf + context_node_nf, out_node_nf=hidden_nf, in_edge_nf=1,
                          hidden_nf=hidden_nf, device=device, act_fn=act_fn, n_layers=n_layers, attention=attention,
                          tanh=tanh, norm_constant=norm_constant, inv_sublayers=inv_sublayers,
@@ -237,9 +242,40 @@ class EGNN_encoder_QM9(nn.Module):
         self.final_mlp = nn.Sequential(nn.Linear(hidden_nf, hidden_nf), nn.SiLU(),
                                        nn.Linear(hidden_nf, out_node_nf * 2 + 1))
         self.in_node_nf, self.out_node_nf = in_node_nf, out_node_nf
+        self.num_classes = in_node_nf - int(include_charges)
+        self.include_charges = int(include_charges)
         self.context_node_nf, self.n_dims, self.device = context_node_nf, n_dims, device
+        self._edges_dict = {}
+        self.validate_masks = validate_masks
+        self._masks = _MaskCache()
+        self.register_buffer("nan_flag", torch.zeros(1, dtype=torch.int32), persistent=False)
         self.to(device)
 
     def _forward(self, xh, node_mask, edge_mask, context):
-        raise NotImplementedError("the VAE encoder is training-only and outside the sampling hot path "
-                                  "(SURVEY §8f rank 1)")
+        self._check_inputs(xh, node_mask)
+        bs, n_nodes, dims = xh.shape
+        nm = node_mask.reshape(bs, n_nodes, 1)
+        if self._wants_grad(xh, context):
+            vel, h_final = wrapper_forward_train(self, None, xh, node_mask, edge_mask, context, False)
+            h_final = train_linear(torch.nn.functional.silu(train_linear(
+                h_final.reshape(bs * n_nodes, -1), self.final_mlp[0].weight, self.final_mlp[0].bias)),
+                self.final_mlp[2].weight, self.final_mlp[2].bias).view(bs, n_nodes, -1) * nm
+        else:
+            with torch.no_grad():
+                batch = self._masks.get(nm, edge_mask, self.validate_masks)
+                xh_flat = xh.reshape(bs * n_nodes, dims).contiguous()
+                ctx = None
+                if context is not None:
+                    ctx = context.reshape(bs * n_nodes, self.context_node_nf).contiguous().float()
+                Fo = self.egnn.out_node_nf
+                out = torch.zeros(bs * n_nodes, self.n_dims + Fo, device=xh.device)
+                self._run(batch, xh_flat, dims, None, None, None, ctx, False, False, Fo, out, self.n_dims + Fo,
+                          scatter=True)
+                vel = out[:, :self.n_dims].reshape(bs, n_nodes, self.n_dims)
+                h_final = self.final_mlp(out[:, self.n_dims:]).view(bs, n_nodes, -1) * nm
+        vel_std = torch.exp(0.5 * h_final[:, :, :1].sum(dim=1, keepdim=True).expand(-1, n_nodes, -1))
+        h_mean = h_final[:, :, 1:1 + self.out_node_nf]
+        h_std = torch.exp(0.5 * h_final[:, :, 1 + self.out_node_nf:])
+        vel_std = torch.where(torch.isnan(vel_std).any(), torch.ones_like(vel_std), vel_std)
+        h_std = torch.where(torch.isnan(h_std).any(), torch.ones_like(h_std), h_std)
+        return vel, vel_std, h_mean, h_std

@@ -1,0 +1,123 @@
+"""One optimisation step of GeoLDM on one or several GPUs (BASELINE config 5).
+
+Host-side mirror of the reference's training inner loop — train_test.py:15-70 (zero_grad, compute_loss_and_nll, backward,
+adaptive clipping, AdamW step, EMA), utils.py:5-66 (EMA, Queue, gradient_clipping) and qm9/models.py:169-175 (optimiser)
+— with the reference's single-process ``DataParallel`` replaced by one process per GPU: every rank evaluates its own
+shard of the batch and gradients are averaged with NCCL all-reduces over flat buckets (dynamics / decoder) before the
+global-norm clipping, so all ranks apply the identical update.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import losses
+
+
+class EMA:
+    """Exponential moving average of the weights (utils.py:5-28)."""
+
+    def __init__(self, beta):
+        self.beta = beta
+
+    def update_average(self, old, new):
+        return new if old is None else old * self.beta + (1 - self.beta) * new
+
+    @torch.no_grad()
+    def update_model_average(self, ma_model, current_model):
+        cur = list(current_model.parameters())
+        avg = list(ma_model.parameters())
+        torch._foreach_mul_(avg, self.beta)
+        torch._foreach_add_(avg, cur, alpha=1 - self.beta)
+
+
+class Queue:
+    """Last max_len gradient norms (utils.py:29-47)."""
+
+    def __init__(self, max_len=50):
+        self.items: List[float] = []
+        self.max_len = max_len
+
+    def __len__(self):
+        return len(self.items)
+
+    def add(self, item):
+        self.items.insert(0, item)
+        if len(self.items) > self.max_len:
+            self.items.pop()
+
+    def mean(self):
+        return np.mean(self.items)
+
+    def std(self):
+        return np.std(self.items)
+
+
+def gradient_clipping(flow, gradnorm_queue: Queue):
+    """Clip the global gradient norm to 1.5 * mean + 2 * std of the recent history (utils.py:50-66)."""
+    max_grad_norm = 1.5 * gradnorm_queue.mean() + 2 * gradnorm_queue.std()
+    grad_norm = torch.nn.utils.clip_grad_norm_(flow.parameters(), max_norm=max_grad_norm, norm_type=2.0)
+    gn = float(grad_norm)
+    gradnorm_queue.add(float(max_grad_norm) if gn > max_grad_norm else gn)
+    return grad_norm
+
+
+def get_optim(args, generative_model):
+    """qm9/models.py:169-175."""
+    return torch.optim.AdamW(generative_model.parameters(), lr=args.lr, amsgrad=True, weight_decay=1e-12)
+
+
+def gradient_buckets(model) -> List[List[torch.nn.Parameter]]:
+    """Parameters that can receive a gradient, grouped per sub-network in reverse registration order (the order in
+    which backward produces them): decoder first, then the denoiser.  The encoder is never in a bucket: its output is
+    detached (en_diffusion.py:1155)."""
+    groups = {"vae.decoder": [], "dynamics": []}
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        for key in groups:
+            if name.startswith(key):
+                groups[key].append(p)
+    return [list(reversed(g)) for g in (groups["vae.decoder"], groups["dynamics"]) if g]
+
+
+def allreduce_gradients(buckets: Iterable[List[torch.nn.Parameter]], group=None) -> int:
+    """Average gradients over ranks: one flat all-reduce per bucket.  Returns the number of bytes reduced.
+    Parameters whose grad is None on this rank contribute zeros (every rank must issue the same collectives)."""
+    world = dist.get_world_size(group)
+    total = 0
+    for params in buckets:
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, grads)):
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+        total += flat.numel() * flat.element_size()
+    return total
+
+
+def train_step(args, model, optim, nodes_dist, x, h, node_mask, edge_mask, context, *, gradnorm_queue: Optional[Queue],
+               model_ema=None, ema: Optional[EMA] = None, buckets=None, group=None, draws=None):
+    """One iteration of train_test.py:train_epoch on this rank's shard.  Returns (nll, grad_norm)."""
+    model.train()
+    optim.zero_grad(set_to_none=True)
+    nll, reg_term, _ = losses.compute_loss_and_nll(args, model, nodes_dist, x, h, node_mask, edge_mask, context,
+                                                   draws=draws)
+    loss = nll + getattr(args, "ode_regularization", 0.0) * reg_term.squeeze()
+    loss.backward()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        allreduce_gradients(buckets if buckets is not None else gradient_buckets(model), group)
+    grad_norm = 0.
+    if getattr(args, "clip_grad", True) and gradnorm_queue is not None:
+        grad_norm = gradient_clipping(model, gradnorm_queue)
+    optim.step()
+    if ema is not None and model_ema is not None and getattr(args, "ema_decay", 0) > 0:
+        ema.update_model_average(model_ema, model)
+    return nll.detach(), grad_norm

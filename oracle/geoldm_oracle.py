@@ -119,19 +119,21 @@ def egnn_param_shapes(in_nf: int, out_nf: int, H: int, L: int, S: int, attention
 
 
 def make_state_dict(cfg: OracleConfig, seed: int = 0, tamed: bool = False,
-                    dtype=torch.float32) -> StateDict:
+                    dtype=torch.float32, encoder: bool = False) -> StateDict:
     """Deterministic random-init weights (numpy PCG64, independent of torch's RNG/version).
 
     Same distributions as the PyTorch defaults the reference relies on: U(-1/sqrt(fan_in), +) for
     Linear weight and bias; coord_mlp.4 is xavier-uniform with gain 1e-3 (egnn_new.py:75-76).
     ``tamed`` applies SURVEY §8c's tamed init (distance columns x1e-5, dynamics embedding_out x0.01).
-    Keys: 'dynamics.egnn.*', 'vae.decoder.egnn.*', 'gamma.gamma'.
+    Keys: 'dynamics.egnn.*', 'vae.decoder.egnn.*', 'gamma.gamma'; with ``encoder=True`` also
+    'vae.encoder.egnn.*' (one block, egnn/models.py:153-160) and 'vae.encoder.final_mlp.{0,2}.*', drawn AFTER the
+    others so that the dynamics/decoder weights of a seed do not depend on the flag.
     """
     rng = np.random.default_rng(seed)
     sd: StateDict = {}
 
-    def fill(prefix, in_nf, out_nf):
-        for key, shape, fan_in, kind in egnn_param_shapes(in_nf, out_nf, cfg.nf, cfg.n_layers,
+    def fill(prefix, in_nf, out_nf, n_layers=cfg.n_layers):
+        for key, shape, fan_in, kind in egnn_param_shapes(in_nf, out_nf, cfg.nf, n_layers,
                                                           cfg.inv_sublayers, cfg.attention):
             if kind == "x":
                 bound = 1e-3 * math.sqrt(6.0 / (shape[0] + shape[1]))
@@ -143,6 +145,14 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0, tamed: bool = False,
     fill("dynamics.egnn.", cfg.dyn_in_nf, cfg.dyn_in_nf)
     fill("vae.decoder.egnn.", cfg.dec_in_nf, cfg.data_node_nf)
     sd["gamma.gamma"] = torch.from_numpy(noise_schedule_gamma(cfg)).to(dtype)
+    if encoder:
+        H = cfg.nf
+        fill("vae.encoder.egnn.", cfg.data_node_nf + cfg.context_node_nf, H, n_layers=1)
+        for key, shape in (("final_mlp.0.weight", (H, H)), ("final_mlp.0.bias", (H,)),
+                           ("final_mlp.2.weight", (2 * cfg.latent_nf + 1, H)),
+                           ("final_mlp.2.bias", (2 * cfg.latent_nf + 1,))):
+            bound = 1.0 / math.sqrt(H)
+            sd["vae.encoder." + key] = torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32)).to(dtype)
     if tamed:
         H = cfg.nf
         for k in list(sd):

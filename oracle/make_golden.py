@@ -61,14 +61,16 @@ def ref_args(cfg: O.OracleConfig, dataset: str):
         ema_decay=0.999, dataset=dataset, remove_h=False)
 
 
-def build_reference(cfg: O.OracleConfig, dataset: str, seed: int, tamed: bool, refmods):
+def build_reference(cfg: O.OracleConfig, dataset: str, seed: int, tamed: bool, refmods, encoder=False,
+                    trainable_ae=False):
     dc, qm, _ = refmods
     info = dc.get_dataset_info(dataset, False)
     args = ref_args(cfg, dataset)
+    args.trainable_ae = trainable_ae
     with contextlib.redirect_stdout(io.StringIO()):
         torch.manual_seed(1234)
         model, _, _ = qm.get_latent_diffusion(args, "cpu", info, None)
-    sd = O.make_state_dict(cfg, seed, tamed)
+    sd = O.make_state_dict(cfg, seed, tamed, encoder=encoder)
     ref_sd = model.state_dict()
     gam = ref_sd["gamma.gamma"].clone()
     missing = [k for k in sd if k not in ref_sd]
