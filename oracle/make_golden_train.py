@@ -113,6 +113,30 @@ def run_case(name, cfg, dataset, nodes, n_max, seed, refmods, full, with_eval, w
     g = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     assert not any(n.startswith("vae.encoder") for n in g), "encoder is detached in EnLatentDiffusion.forward"
     arrays.update(summarise(g, full))
+    if not full:
+        # the same step in float64 (same weights, inputs and draws): the exact gradients both fp32 runs approximate
+        m64 = model.double()
+        for p in m64.parameters():
+            p.grad = None
+        d64 = {k: v.double() for k, v in rec.draws.items()}
+        seq = iter([d64["eps_t"]])
+        o_v, o_l, o_r = m64.vae.sample_combined_position_feature_noise, m64.sample_combined_position_feature_noise, torch.randint
+        m64.vae.sample_combined_position_feature_noise = lambda *a, **k: d64["eps_enc"]
+        m64.sample_combined_position_feature_noise = lambda *a, **k: next(seq)
+        torch.randint = lambda *a, **k: rec.draws["t_int"]
+        try:
+            h64 = {k: v.double() for k, v in h.items()}
+            nll64, _, _ = ref_losses.compute_loss_and_nll(args, m64, nodes_dist, x.double(), h64, nm.double(),
+                                                          em.double(), None if ctx is None else ctx.double())
+            nll64.backward()
+        finally:
+            m64.vae.sample_combined_position_feature_noise, m64.sample_combined_position_feature_noise = o_v, o_l
+            torch.randint = o_r
+        g64 = {n: p.grad.detach().clone() for n, p in m64.named_parameters() if p.grad is not None}
+        s64 = summarise(g64, False)
+        arrays.update({"gmax64": s64["gmax"], "gl264": s64["gl2"], "ghead64": s64["ghead"],
+                       "train_loss64": nll64.detach()})
+        model.float()
     with Recorder(model) as rec, torch.no_grad():
         torch.manual_seed(8)
         per_mol = model(x, h, nm, em.view(len(nodes), -1), ctx)

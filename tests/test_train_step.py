@@ -13,6 +13,7 @@ from tests.helpers import build_cuda_model, load_golden
 
 LOSS_TOL = 1e-5
 GRAD_TOL = 2e-5
+GRAD_TOL64 = 2e-5      # vs the float64 run of the reference (full-size case)
 
 
 def _rel(a, b):
@@ -67,14 +68,30 @@ def _check_case(name, device, monkeypatch=None):
     if "names" in A:
         names = [str(s) for s in np.asarray(A["names"])]
         assert sorted(grads) == names
+        # Same well-posed form as the forward gate (helpers.assert_parity): the reference's own fp32 gradients carry
+        # rounding noise (up to 3.6e-5 on a 5e-6-sized attention-bias gradient that is a cancelling sum over all
+        # edges), so each tensor is gated by  err(ours, ref32) <= GRAD_TOL + err(ref32, ref64)  and
+        # err(ours, ref64) <= GRAD_TOL64.
+        worst64, floor_at_worst = 0.0, 0.0
         for i, n in enumerate(names):
-            gp, ref_max = grads[n], float(A["gmax"][i])
+            gp = grads[n]
             head = gp.flatten()[:256].double().cpu()
-            e = max(abs(float(gp.abs().max()) - ref_max) / ref_max,
-                    abs(float(gp.double().norm()) - float(A["gl2"][i])) / float(A["gl2"][i]),
-                    float((head - A["ghead"][i][:head.numel()].double()).abs().max()) / ref_max)
-            if e > worst:
-                worst, wname = e, n
+
+            def err(mx, l2, hd):
+                mx, l2 = float(mx), float(l2)
+                return max(abs(float(gp.abs().max()) - mx) / mx, abs(float(gp.double().norm()) - l2) / l2,
+                           float((head - hd[:head.numel()].double()).abs().max()) / mx)
+            e32 = err(A["gmax"][i], A["gl2"][i], A["ghead"][i])
+            e64 = err(A["gmax64"][i], A["gl264"][i], A["ghead64"][i])
+            floor = max(abs(float(A["gmax"][i]) - float(A["gmax64"][i])) / float(A["gmax64"][i]),
+                        float((A["ghead"][i].double() - A["ghead64"][i].double()).abs().max()) / float(A["gmax64"][i]))
+            worst64 = max(worst64, e64)
+            if e32 - floor > worst - floor_at_worst:
+                worst, wname, floor_at_worst = e32, n, floor
+        print(f"[train] {name}: worst grad vs fp64 reference {worst64:.2e}; vs fp32 reference {worst:.2e} "
+              f"(reference's own fp32 noise there {floor_at_worst:.2e})")
+        assert worst64 < GRAD_TOL64
+        worst = max(0.0, worst - floor_at_worst)
     else:
         ref = {k[2:]: v for k, v in A.items() if k.startswith("g.")}
         assert sorted(grads) == sorted(ref)
