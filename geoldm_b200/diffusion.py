@@ -137,6 +137,12 @@ class EnLatentDiffusion(nn.Module):
         self._graphs = {}
         self.use_cuda_graph = True
 
+    def __getstate__(self):
+        d = self.__dict__.copy()                 # coefficient table / captured graphs are rebuilt lazily
+        d["_coef_cache"], d["_graphs"] = None, {}
+        d.pop("_last_graph", None)
+        return d
+
     def check_issues_norm_values(self, num_stdevs=8):
         sigma_0 = math.sqrt(1.0 / (1.0 + math.exp(-float(self.gamma.gamma[0]))))
         max_norm = max(self.norm_values[1], self.norm_values[2])

@@ -45,6 +45,12 @@ def _stream(device):
 
 
 class _EgnnWrapper(nn.Module):
+    def __getstate__(self):
+        d = self.__dict__.copy()                 # caches (packed masks, scratch) are per-instance and rebuilt lazily
+        d["_masks"] = _MaskCache()
+        d.pop("_bufs", None)
+        return d
+
     def get_adj_matrix(self, n_nodes, batch_size, device):
         """Reference API (egnn/models.py:115-134).  The CUDA path never materialises the edge list;
         provided (vectorised) for callers that want it."""

@@ -132,6 +132,13 @@ class EGNN(nn.Module):
     def _params_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle (the reference clones the model for its EMA copy, main_qm9.py:227-231): derived
+        device images and scratch are rebuilt on demand, never copied."""
+        d = self.__dict__.copy()
+        d["_pack"], d["_pack_key"], d["_ws"] = None, None, None
+        return d
+
     @torch.no_grad()
     def packed(self):
         """(ctypes EgnnWeights, keep-alive list).  Rebuilt when any parameter changed."""

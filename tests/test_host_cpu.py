@@ -125,3 +125,16 @@ def test_step_table_matches_oracle_coefficients():
         assert table[s, 0] == a and table[s, 1] == c and table[s, 2] == n
         assert table[s, 3] == torch.tensor(float(s + 1)) / 1000
     assert table.shape == (1001, 4) and table[1000, 3] == 0
+
+
+def test_model_deepcopy_for_ema():
+    """main_qm9.py:227-231 clones the model for the EMA weights; cached device images must not block that."""
+    import copy
+    from tests.helpers import build_cuda_model
+    from oracle import geoldm_oracle as O
+    cfg = O.OracleConfig(nf=32, n_layers=1)
+    model = build_cuda_model(cfg, O.make_state_dict(cfg, 0), device="cpu")
+    clone = copy.deepcopy(model)
+    a, b = model.state_dict(), clone.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert all(p.data_ptr() != q.data_ptr() for p, q in zip(model.parameters(), clone.parameters()) if p.numel())
