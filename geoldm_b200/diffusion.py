@@ -185,13 +185,16 @@ class EnLatentDiffusion(nn.Module):
 
     @torch.no_grad()
     def sample_latent_ragged(self, batch: RaggedBatch, context_ragged=None, fix_noise=False, noise=None,
-                             seed: int = 0, n_steps: Optional[int] = None, trace: Optional[list] = None):
+                             seed: int = 0, n_steps: Optional[int] = None, trace: Optional[list] = None,
+                             frame_cb=None):
         """a13+a14 on ragged state.  Returns z_xh [N, 3+latent] = (x, latent h) after p(x,h|z0).
 
         noise: None -> device Philox keyed by (seed, batch.mol_id) [fix_noise: every molecule uses key 0];
                tensor [T+2, N, D] (ragged, fp32, CUDA) -> injected draws in call order (init, steps, z0->x).
         n_steps: run only the first n_steps of the loop and return z (testing).
-        trace: list receiving (z_t, eps_hat, z_s) clones per step (testing; disables the CUDA graph)."""
+        trace: list receiving (z_t, eps_hat, z_s) clones per step (testing; disables the CUDA graph).
+        frame_cb: callable(s, z) invoked on the host after the step that produced z_s (s = T-1 ... 0); it may enqueue
+                  copies of z on the current stream (sample_chain)."""
         L = _lib.lib()
         dev = batch.mol_off.device
         D = self.n_dims + self.in_node_nf
@@ -228,14 +231,18 @@ class EnLatentDiffusion(nn.Module):
         advance(0, 1)
         steps = T if n_steps is None else min(n_steps, T)
         if trace is not None or not self.use_cuda_graph or steps < 3:
-            for _ in range(steps):
+            for k in range(steps):
                 if trace is not None:
                     z_prev = z.clone()
                 one_step()
                 if trace is not None:
                     trace.append((z_prev, eps.clone(), z.clone()))
+                if frame_cb is not None:
+                    frame_cb(T - 1 - k, z)
         else:
             one_step()              # warm-up outside capture (lazy module init, workspace allocation)
+            if frame_cb is not None:
+                frame_cb(T - 1, z)
             graph = torch.cuda.CUDAGraph()
             cap = torch.cuda.Stream(device=dev)
             cap.wait_stream(torch.cuda.current_stream(dev))
@@ -246,8 +253,10 @@ class EnLatentDiffusion(nn.Module):
                     one_step()
             torch.cuda.current_stream(dev).wait_stream(cap)
             st = _stream(dev)
-            for _ in range(steps - 1):
+            for k in range(steps - 1):
                 graph.replay()
+                if frame_cb is not None:
+                    frame_cb(T - 2 - k, z)
             self._last_graph = graph
         if n_steps is not None and steps < T:
             return z
@@ -295,6 +304,42 @@ class EnLatentDiffusion(nn.Module):
             x = x - (x.sum(1, keepdim=True) / nn_) * node_mask
             z_xh = torch.cat([x, z_xh[:, :, self.n_dims:]], dim=2)
         return self.vae.decode(z_xh, node_mask, edge_mask, context)
+
+    @torch.no_grad()
+    def sample_chain(self, n_samples, n_nodes, node_mask, edge_mask, context, keep_frames=None, *, noise=None, seed=0):
+        """Sampling with intermediate states kept and decoded (en_diffusion.py:797-838 and :1206-1232): returns
+        [keep_frames * n_samples, n_nodes, 3 + vae.in_node_nf]; frame 0 is the final sample, frame k the latent after the
+        last step s with (s * keep_frames) // T == k.  Same loop and CUDA graph as ``sample``; frames are copied out
+        between graph replays, then decoded one frame at a time like the reference."""
+        if not node_mask.is_cuda:
+            raise _lib.GeoldmError("geoldm_b200 has no CPU path: masks must be CUDA tensors")
+        bs, n, T = n_samples, n_nodes, self.T
+        kf = T if keep_frames is None else keep_frames
+        assert kf <= T
+        node_mask = node_mask.reshape(bs, n, 1)
+        dev = node_mask.device
+        batch = pack_from_masks(node_mask, edge_mask, validate=self.dynamics.validate_masks)
+        src = batch.node_src.long()
+        D = self.n_dims + self.in_node_nf
+        ctx_r = None if context is None else context.reshape(bs * n, -1)[src].contiguous().float()
+        noise_r = None
+        if noise is not None:
+            noise_r = noise.to(dev, torch.float32).reshape(noise.shape[0], bs * n, D)[:, src].contiguous()
+        chain_r = torch.zeros(kf, batch.n_node, D, device=dev)
+
+        def keep(s, z):
+            idx = (s * kf) // T
+            if s == 0 or ((s - 1) * kf) // T != idx:          # the reference overwrites; the smallest s of a frame wins
+                chain_r[idx].copy_(z)
+
+        chain_r[0] = self.sample_latent_ragged(batch, ctx_r, noise=noise_r, seed=seed, frame_cb=keep)
+        out = torch.zeros(kf, bs, n, self.vae.in_node_nf + self.vae.n_dims, device=dev)
+        for i in range(kf):
+            z_xh = torch.zeros(bs * n, D, device=dev)
+            z_xh[src] = chain_r[i]
+            x, h = self.vae.decode(z_xh.view(bs, n, D), node_mask, edge_mask, context)
+            out[i] = torch.cat([x, h['categorical'].to(x.dtype), h['integer'].to(x.dtype)], dim=2)
+        return out.view(kf * bs, n, -1)
 
     @torch.no_grad()
     def sample_p_zs_given_zt(self, s, t, zt, node_mask, edge_mask, context, fix_noise=False, *, noise=None, seed=0):

@@ -181,6 +181,14 @@ int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, con
  * zeroes C; lda/ldb multiples of 4).  Forward and input-gradient GEMMs of a Linear layer use geoldm_linear. */
 int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
                    void* stream);
+/* ---- evaluation side: bond-order stability of a ragged batch of molecules.
+ * Replaces the Python double loop of qm9/analyze.py:209-245 (check_stability) + qm9/bond_analyze.py:101-146.
+ * x [N][3] fp32, atom_type [N] in [0, n_types), mol_off [n_mol+1]; thr [3][n_types][n_types] = single/double/triple
+ * thresholds in pm incl. margins for the ORDERED pair (first, second), negative = no entry; allowed[t] = bitmask of
+ * allowed valences; sorted_pair 0: (type_i, type_j) with i < j (QM9), 1: pair sorted by type index (GEOM).
+ * Outputs: nr_bonds [N] (may be NULL), n_stable [n_mol] = number of atoms with an allowed valence. */
+int geoldm_stability(int n_mol, const int* mol_off, const float* x, const int* atom_type, int n_types, const float* thr,
+                     const int* allowed, int sorted_pair, int* nr_bonds, int* n_stable, void* stream);
 /* debug (GEOLDM_TC_DEBUG & 32): read+reset cycle counters of the MMA-issuing thread of CTA 0:
  * {total, wait acc_empty, wait a_full, wait w_full, launches, tiles, 0, 0}; synchronises the device */
 int geoldm_tc_read_stats(unsigned long long* host_out);
