@@ -9,8 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libgeoldm_b200.so")
 
 MAX_LAYERS, MAX_SUBLAYERS = 16, 4
-MMA_FP32_SIMT, MMA_3XTF32, MMA_TF32, MMA_BF16 = 0, 1, 2, 3
-MMA_MODES = {"fp32": MMA_FP32_SIMT, "3xtf32": MMA_3XTF32, "tf32": MMA_TF32, "bf16": MMA_BF16}
+MMA_FP32_SIMT, MMA_3XTF32, MMA_TF32, MMA_BF16, MMA_3XF16 = 0, 1, 2, 3, 4
+MMA_MODES = {"fp32": MMA_FP32_SIMT, "3xtf32": MMA_3XTF32, "tf32": MMA_TF32, "bf16": MMA_BF16,
+             "3xf16": MMA_3XF16}
 
 fp = C.c_void_p  # device pointers travel as integers
 
@@ -66,6 +67,8 @@ _SIGS = {
                                 C.c_int, fp]),
     "geoldm_tc_pack_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "geoldm_tc_pack": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
+    "geoldm_tc_pack16_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "geoldm_tc_pack16": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
     "geoldm_linear_tc": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, C.c_int,
                                    fp, C.c_int, fp]),
     "geoldm_tc_selftest": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_int, fp, fp, fp]),

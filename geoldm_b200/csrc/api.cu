@@ -62,7 +62,7 @@ static int check_cfg(const geoldm_egnn_config* cfg) {
                  cfg->inv_sublayers, GEOLDM_MAX_SUBLAYERS);
   GEOLDM_REQUIRE(cfg->hidden_nf % 32 == 0, "hidden_nf %d must be a multiple of 32", cfg->hidden_nf);
   GEOLDM_REQUIRE(cfg->agg_div != 0.f, "agg_div must be non-zero");
-  GEOLDM_REQUIRE(cfg->mma_mode >= 0 && cfg->mma_mode <= 3, "bad mma_mode %d", cfg->mma_mode);
+  GEOLDM_REQUIRE(cfg->mma_mode >= 0 && cfg->mma_mode <= 4, "bad mma_mode %d", cfg->mma_mode);
   return 0;
 }
 
@@ -73,7 +73,7 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   cudaStream_t st = (cudaStream_t)stream;
   const int N = b->n_node, H = cfg->hidden_nf;
   const bool tcore = cfg->mma_mode != GEOLDM_MMA_FP32_SIMT;
-  const int terms = cfg->mma_mode == GEOLDM_MMA_TF32 ? 1 : 3;
+  const int terms = cfg->mma_mode == GEOLDM_MMA_TF32 ? 1 : cfg->mma_mode == GEOLDM_MMA_3XF16 ? 16 : 3;
   GEOLDM_REQUIRE(cfg->mma_mode != GEOLDM_MMA_BF16, "mma_mode bf16 is not implemented yet");
   if (N == 0) return 0;
   Workspace ws = carve(workspace, N, H);

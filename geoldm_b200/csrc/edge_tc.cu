@@ -769,6 +769,7 @@ int launch_h(int H, const TcArgs& a, cudaStream_t st) {
 
 int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                    const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
+  if (cfg.mma_mode == GEOLDM_MMA_3XF16) return launch_edge_tc16(cfg, w, b, equiv, pq, pq_ld, x, x0, out, st);
   GEOLDM_REQUIRE(b.tile_m == TM, "edge_tc: batch tile_m=%d, kernel needs %d", b.tile_m, TM);
   GEOLDM_REQUIRE(w.tc_pack != nullptr, "edge_tc: tc_pack missing (weights not packed for the tensor-core path)");
   GEOLDM_REQUIRE(equiv || !cfg.attention || w.b_out != nullptr, "edge_tc: attention needs b_out");
@@ -788,6 +789,7 @@ int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, cons
 int launch_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
                      const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out, int m,
                      cudaStream_t st) {
+  if (terms == 16) return launch_linear_tc16(H, a1, k1, a2, k2, a2_div, w_pack, n_blocks, bias, res, epi, out, m, st);
   GEOLDM_REQUIRE(k1 % BK == 0 && k2 % BK == 0 && k1 + k2 > 0, "linear_tc: k1=%d k2=%d must be multiples of %d", k1, k2, BK);
   GEOLDM_REQUIRE(w_pack != nullptr, "linear_tc: w_pack missing");
   TcArgs a{};
@@ -802,6 +804,7 @@ int launch_linear_tc(int H, int terms, const float* a1, int k1, const float* a2,
 // self-test: out[rows][H] = pq[edge_i[row]][0:H] * W^T   (K = H)
 int launch_tc_selftest(int H, int terms, const float* pq, const int* edge_i, const int* tile_row, int n_tile,
                        int n_rows, const void* w_pack, float* out, cudaStream_t st) {
+  if (terms == 16) return launch_tc16_selftest(H, pq, edge_i, tile_row, n_tile, n_rows, w_pack, out, st);
   TcArgs a{};
   a.n_tile = n_tile; a.n_rows = n_rows; a.tile_row = tile_row; a.n_blocks = 1; a.n_slabs = H / BK; a.terms = terms;
   a.pq = pq; a.pq_ld = 2 * H; a.edge_i = edge_i; a.w_pack = reinterpret_cast<const float*>(w_pack); a.out = out; a.ldo = H;

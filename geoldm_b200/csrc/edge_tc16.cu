@@ -1,0 +1,669 @@
+// tcgen05 / TMEM tensor-core kernels, fp16-split arithmetic (GEOLDM_MMA_3XF16).
+//
+// Same fused kernels as edge_tc.cu (GCL / EQUIV / DENSE / RAW, same roles, same shared-memory images, CTA pairs with
+// cta_group::2 MMAs), with the fp32-equivalent product formed from fp16 halves instead of tf32 halves:
+//     a = a_hi + a_lo,  w * 2^e = w_hi + w_lo   (all four fp16, 11 significant bits each, like tf32)
+//     a * w = 2^-e (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi)                 fp32 accumulation in TMEM
+// kind::f16 MMAs run at twice the tf32 rate and a 128-byte swizzle row holds 64 K-columns instead of 32, so a tile
+// needs half the k-slabs, half the MMA time and half the operand bytes per K.  That frees the second 256-column
+// TMEM region (the tf32 kernel needs it for its K-split): here consecutive tiles ALTERNATE between the two regions,
+// so the fused tail of tile t overlaps the MMAs of tile t+1 and the A generation of tile t+2.
+// The weight images carry a power-of-two scale 2^e (chosen by geoldm_tc_pack16 so that max|w| 2^e is in [2^13, 2^14)):
+// it keeps w_lo out of the fp16 subnormal range; the epilogue folds 2^-e into the round-toward-zero compensation
+// factor.  Activations are not scaled (|a| < 65504 required; a_lo below 2^-14 is subnormal: absolute error <= 2^-25).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace geoldm {
+namespace {
+using namespace tc;
+
+constexpr int TM = 128;          // rows per tile (TMEM lanes)
+constexpr int BK = 64;           // k-slab: 64 fp16 = 128 bytes per row = one swizzle row
+constexpr int NTHREADS = 576;    // 8 epilogue + 8 producer warps + loader + MMA
+constexpr int NWS = 3;           // W pipeline stages
+constexpr int EPI_T = 256, PROD_T = 256;
+constexpr int WARP_LOAD = 16, WARP_MMA = 17;
+constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
+constexpr uint32_t PACK_HDR = 128;   // bytes: float inv_scale at offset 0
+constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;   // see edge_tc.cu; re-measured for kind::f16 with scripts/tc_bias_probe.py
+
+struct Args {
+  int n_tile, n_rows;
+  const int* tile_row;
+  int n_blocks;
+  int n_slabs;              // K / 64
+  const float* pq; int pq_ld;
+  const float* x; const float* x0;
+  const int* edge_i; const int* edge_j;
+  const float* w_rd;
+  const float* a1; const float* a2; int k1, k2; float a2_div;
+  const uint8_t* w_pack;    // header + [block][slab][N-half][hi image | lo image]
+  const float* b2; const float* w_out; const float* b_out; const float* res;
+  float* out; int ldo; int epi;
+  float norm_constant, coords_range;
+  int attention, use_tanh;
+  float rz_scale;           // 1 + RZ_BIAS_PER_MMA * (#MMAs accumulated per output)
+};
+
+template <int H, int MODE>
+struct Smem {
+  static constexpr int NAS = (MODE == 0) ? 2 : 3;
+  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 36 * 4 : 0u;
+  static constexpr uint32_t NH = H / 2;
+  static constexpr uint32_t W_IMG = NH * 128u;
+  static constexpr uint32_t W_STAGE = 2u * W_IMG;
+  static constexpr uint32_t A_STAGE = 2u * TM * 128u;
+  static constexpr uint32_t OFF_W = 0;
+  static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
+  static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;
+  static constexpr uint32_t OFF_SI = OFF_T + T_BYTES;
+  static constexpr uint32_t OFF_PS = OFF_SI + TM * 4;
+  static constexpr uint32_t OFF_DX = OFF_PS + 8 * 34 * 4;
+  static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;
+  static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;
+  static constexpr uint32_t OFF_BAR = OFF_VEC + 2 * H * 4;
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + (3 * NWS + 2 * NAS + 4) * 8;
+  static constexpr uint32_t BYTES = OFF_TMEM + 16;
+  static constexpr uint32_t ALLOC = BYTES + 1024;
+};
+
+// kind::f16 (fp16 inputs), fp32 accumulate, A and B K-major, M = 256 over a CTA pair, N = n
+__host__ __device__ constexpr uint32_t make_idesc_f16_m256(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// 8 fp32 -> 8 fp16 hi + 8 fp16 lo (lo = fp16(v - hi), exact subtraction), packed for one 16-byte swizzle chunk
+__device__ __forceinline__ void split_f16x8(const float (&e)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(e[2 * i] - hf.x, e[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int H, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
+  using S = Smem<H, MODE>;
+  constexpr int NAS = S::NAS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* w_full = bars;                            // [NWS]
+  uint64_t* w_empty = bars + NWS;                     // [NWS]
+  uint64_t* a_full = bars + 2 * NWS;                  // [NAS]
+  uint64_t* a_empty = bars + 2 * NWS + NAS;           // [NAS]
+  uint64_t* acc_full = bars + 2 * NWS + 2 * NAS;      // [2]  accumulator region r holds a complete tile
+  uint64_t* acc_empty = bars + 2 * NWS + 2 * NAS + 2; // [2]  region r drained by the epilogue
+  uint64_t* w_peer = bars + 2 * NWS + 2 * NAS + 4;    // [NWS] the peer CTA's N-half of the W stage has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  constexpr uint16_t cmask = 3;
+  const int n_tile_pad = (a.n_tile + 1) / 2 * 2;
+  const int work_per_block = n_tile_pad / 2;          // a work item = 256 rows (one 128-row tile per CTA of the pair)
+  const int n_workers = (int)gridDim.x / 2;
+  const int worker = (int)blockIdx.x / 2;
+  const int total_work = work_per_block * a.n_blocks;
+  const int n_iter = (total_work + n_workers - 1) / n_workers;
+
+  if (tid == 0) {
+    for (int s = 0; s < NWS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&w_peer[s], 1); }
+    for (int s = 0; s < NAS; ++s) { mbar_init(&a_full[s], 2 * PROD_T / 32); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * EPI_T / 32); }
+    fence_barrier_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc2(tmem_slot, 512);
+  if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+    float* vec = reinterpret_cast<float*>(smem + S::OFF_VEC);
+    for (int c = tid; c < H; c += NTHREADS) { vec[c] = a.b2[c]; vec[H + c] = a.w_out[c]; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_of = [&](int iter, int& tile, int& nb, int& row0, int& nrows) {
+    const int work = iter * n_workers + worker;
+    nb = work / work_per_block;
+    tile = 2 * (work % work_per_block) + (int)crank;
+    if (nb >= a.n_blocks || tile >= a.n_tile) {
+      nb = nb >= a.n_blocks ? a.n_blocks - 1 : nb;
+      row0 = 0; nrows = 0;
+      return;
+    }
+    row0 = a.tile_row ? a.tile_row[tile] : tile * TM;
+    nrows = (a.tile_row ? a.tile_row[tile + 1] : min(a.n_rows, row0 + TM)) - row0;
+  };
+
+  if (warp == WARP_LOAD) {
+    // =========================== W-stage loader (TMA engine) ==============================================
+    if (lane == 0) {
+      uint32_t wit = 0;
+      for (int iter = 0; iter < n_iter; ++iter) {
+        int tile, nb, row0, nrows;
+        tile_of(iter, tile, nb, row0, nrows);
+        const uint8_t* src = a.w_pack + PACK_HDR + (size_t)nb * a.n_slabs * 2 * S::W_STAGE;
+        for (int s = 0; s < a.n_slabs; ++s, ++wit) {
+          const int st = wit % NWS;
+          mbar_wait(&w_empty[st], ((wit / NWS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&w_full[st], S::W_STAGE);
+          bulk_g2s(smem + S::OFF_W + st * S::W_STAGE, src + (size_t)(2 * s + crank) * S::W_STAGE, S::W_STAGE, &w_full[st]);
+        }
+      }
+    } else if (lane == 1 && crank == 1) {
+      uint32_t wit = 0;
+      for (int iter = 0; iter < n_iter; ++iter)
+        for (int s = 0; s < a.n_slabs; ++s, ++wit) {
+          const int st = wit % NWS;
+          mbar_wait(&w_full[st], (wit / NWS) & 1);
+          mbar_arrive_remote(&w_peer[st], 0);
+        }
+    }
+  } else if (warp == WARP_MMA) {
+    // =========================== MMA issuer (leader CTA) ==================================================
+    if (crank == 0) {
+      const uint32_t idesc = make_idesc_f16_m256(H);
+      uint32_t wit = 0, ait = 0;
+      for (int iter = 0; iter < n_iter; ++iter) {
+        const int region = iter & 1;
+        mbar_wait_cluster(&acc_empty[region], ((iter >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + region * 256;
+        for (int s = 0; s < a.n_slabs; ++s, ++ait, ++wit) {
+          const int ast = ait % NAS, wst = wit % NWS;
+          mbar_wait_cluster(&a_full[ast], (ait / NAS) & 1);
+          mbar_wait(&w_full[wst], (wit / NWS) & 1);
+          mbar_wait_cluster(&w_peer[wst], (wit / NWS) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(smem + S::OFF_A + ast * S::A_STAGE);
+            const uint32_t a_lo = a_hi + TM * 128;
+            const uint32_t w_hi = smem_u32(smem + S::OFF_W + wst * S::W_STAGE);
+            const uint32_t w_lo = w_hi + S::W_IMG;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t da_hi = make_smem_desc_sw128(a_hi + kk * 32), da_lo = make_smem_desc_sw128(a_lo + kk * 32);
+              const uint64_t dw_hi = make_smem_desc_sw128(w_hi + kk * 32), dw_lo = make_smem_desc_sw128(w_lo + kk * 32);
+              mma_f16_pair(d_tmem, da_lo, dw_hi, idesc, (s | kk) != 0);
+              mma_f16_pair(d_tmem, da_hi, dw_lo, idesc, 1);
+              mma_f16_pair(d_tmem, da_hi, dw_hi, idesc, 1);
+            }
+            mma_commit_pair(&w_empty[wst], cmask);
+            mma_commit_pair(&a_empty[ast], cmask);
+            if (s == a.n_slabs - 1) mma_commit_pair(&acc_full[region], cmask);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // =========================== A producers (256 threads) ================================================
+    const int pt = tid - EPI_T;
+    const int chunk = pt & 7;        // 16-byte chunk: k = 8*chunk .. 8*chunk+7 inside the slab
+    const int rbase = pt >> 3;       // rows rbase + 32 p
+    uint32_t it = 0;
+    for (int iter = 0; iter < n_iter; ++iter) {
+      int tile, nb, row0, nrows;
+      tile_of(iter, tile, nb, row0, nrows);
+      const float* pP[4];
+      const float* pQ[4];
+      float rr[4], dd[4];
+      bool valid[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int r = rbase + 32 * p;
+        valid[p] = r < nrows;
+        pP[p] = nullptr; pQ[p] = nullptr; rr[p] = 0.f; dd[p] = 0.f;
+        if (valid[p]) {
+          if (MODE == MODE_DENSE) {
+            pP[p] = a.a1 + (size_t)(row0 + r) * a.k1 + 8 * chunk;
+            pQ[p] = a.a2 ? a.a2 + (size_t)(row0 + r) * a.k2 + 8 * chunk : nullptr;
+          } else {
+            const int i = a.edge_i[row0 + r];
+            pP[p] = a.pq + (size_t)i * a.pq_ld + 8 * chunk;
+            if (MODE != MODE_RAW) {
+              const int j = a.edge_j[row0 + r];
+              pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 8 * chunk;
+              const float* xi = a.x + 3 * (size_t)i;
+              const float* xj = a.x + 3 * (size_t)j;
+              const float* yi = a.x0 + 3 * (size_t)i;
+              const float* yj = a.x0 + 3 * (size_t)j;
+              const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+              const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
+              rr[p] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+              dd[p] = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+            }
+          }
+        }
+      }
+      for (int s = 0; s < a.n_slabs; ++s, ++it) {
+        const int st = it % NAS;
+        const int k0 = s * BK;
+        float wr[8], wd[8];
+        if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 8 * chunk));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 8 * chunk + 4));
+          const float4 d0 = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 8 * chunk));
+          const float4 d1 = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 8 * chunk + 4));
+          wr[0] = r0.x; wr[1] = r0.y; wr[2] = r0.z; wr[3] = r0.w; wr[4] = r1.x; wr[5] = r1.y; wr[6] = r1.z; wr[7] = r1.w;
+          wd[0] = d0.x; wd[1] = d0.y; wd[2] = d0.z; wd[3] = d0.w; wd[4] = d1.x; wd[5] = d1.y; wd[6] = d1.z; wd[7] = d1.w;
+          if (s + 1 < a.n_slabs) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+              if (valid[p]) { prefetch_l1(pP[p] + k0 + BK); prefetch_l1(pQ[p] + k0 + BK); }
+          }
+        }
+        bool waited = false;
+        uint8_t* a_hi = smem + S::OFF_A + st * S::A_STAGE;
+        uint8_t* a_lo = a_hi + TM * 128;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {          // two rows at a time: bounds the registers held by loads in flight
+          float4 v[2][2], q[2][2];
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int p = 2 * ph + pp;
+            v[pp][0] = v[pp][1] = q[pp][0] = q[pp][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[p]) {
+              if (MODE == MODE_DENSE) {
+                if (k0 < a.k1) {
+                  v[pp][0] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
+                  v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
+                } else {
+                  q[pp][0] = __ldg(reinterpret_cast<const float4*>(pQ[p] + (k0 - a.k1)));
+                  q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + (k0 - a.k1) + 4));
+                }
+              } else {
+                v[pp][0] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
+                v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
+                if (MODE != MODE_RAW) {
+                  q[pp][0] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0));
+                  q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0 + 4));
+                }
+              }
+            }
+          }
+          if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; }
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int p = 2 * ph + pp;
+            const int r = rbase + 32 * p;
+            const float vv[8] = {v[pp][0].x, v[pp][0].y, v[pp][0].z, v[pp][0].w, v[pp][1].x, v[pp][1].y, v[pp][1].z, v[pp][1].w};
+            const float qq[8] = {q[pp][0].x, q[pp][0].y, q[pp][0].z, q[pp][0].w, q[pp][1].x, q[pp][1].y, q[pp][1].z, q[pp][1].w};
+            float e[8];
+            if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                e[c] = silu(fmaf(wd[c], dd[p], fmaf(wr[c], rr[p], vv[c] + qq[c])));
+                if (!valid[p]) e[c] = 0.f;
+              }
+            } else if (MODE == MODE_DENSE) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                if (k0 < a.k1) e[c] = vv[c];
+                else e[c] = (a.a2_div != 1.0f) ? __fdiv_rn(qq[c], a.a2_div) : qq[c];
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) e[c] = vv[c];
+            }
+            uint4 hi, lo;
+            split_f16x8(e, hi, lo);
+            const uint32_t off = sw128_off(r, chunk);
+            *reinterpret_cast<uint4*>(a_hi + off) = hi;
+            *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { if (crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+      }
+    }
+  } else {
+    // ============= epilogue (warps 0-7: thread = (TMEM lane = row, column half)) ==========================
+    const int r = (warp & 3) * 32 + lane;
+    const int hf = warp >> 2;
+    constexpr int HC = H / 2;
+    constexpr int NCH = HC / 32;
+    int* s_i = reinterpret_cast<int*>(smem + S::OFF_SI);
+    int* s_ps = reinterpret_cast<int*>(smem + S::OFF_PS);
+    float* s_dx = reinterpret_cast<float*>(smem + S::OFF_DX);
+    float* s_dot = reinterpret_cast<float*>(smem + S::OFF_DOT);
+    const float* s_b2 = reinterpret_cast<const float*>(smem + S::OFF_VEC) + hf * HC;
+    const float* s_wo = s_b2 + H;
+    const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * HC;
+    // 2^-e of the weight images times the round-toward-zero compensation
+    const float scale = __ldg(reinterpret_cast<const float*>(a.w_pack)) * a.rz_scale;
+    auto release_acc = [&](int region) {
+      __syncwarp();
+      if (lane == 0) { if (crank != 0) mbar_arrive_remote(&acc_empty[region], 0); else mbar_arrive(&acc_empty[region]); }
+    };
+    for (int iter = 0; iter < n_iter; ++iter) {
+      int tile, nb, row0, nrows;
+      tile_of(iter, tile, nb, row0, nrows);
+      const bool valid = r < nrows;
+      const int region = iter & 1;
+      int my_i = -1;
+      float ux = 0.f, uy = 0.f, uz = 0.f;
+      if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+        if (valid) {
+          my_i = a.edge_i[row0 + r];
+          if (MODE == MODE_EQUIV && hf == 0) {
+            EdgeGeom g = edge_geom(a.x, a.x0, my_i, a.edge_j[row0 + r], a.norm_constant);
+            ux = g.ux; uy = g.uy; uz = g.uz;
+          }
+        }
+        if (hf == 0) s_i[r] = my_i;
+      }
+      mbar_wait(&acc_full[region], (iter >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tlane + region * 256;
+
+      if (MODE == MODE_DENSE || MODE == MODE_RAW) {
+        float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
+        const float* rrow = (MODE == MODE_DENSE && a.epi == 2) ? a.res + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC : nullptr;
+        const float* bias = (MODE == MODE_DENSE && a.b2) ? a.b2 + nb * H + hf * HC : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cc * 32, v);
+          tmem_ld_wait();
+          if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }     // registers hold the last chunk
+          if (valid) {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float o[4] = {__uint_as_float(v[c4 * 4]) * scale, __uint_as_float(v[c4 * 4 + 1]) * scale,
+                            __uint_as_float(v[c4 * 4 + 2]) * scale, __uint_as_float(v[c4 * 4 + 3]) * scale};
+              if (bias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + c4 * 4));
+                o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+              }
+              if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
+              if (rrow) {
+                const float4 rs = __ldg(reinterpret_cast<const float4*>(rrow + cc * 32 + c4 * 4));
+                o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
+              }
+              *reinterpret_cast<float4*>(orow + cc * 32 + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      } else {
+        // ---- pass 1: m = SiLU(scale * D + b2), partial row dot with w_att / w6 over this thread's column half -----
+        float dot = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b2 + cc * 32 + c4 * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wo + cc * 32 + c4 * 4);
+            const float m0 = silu(fmaf(__uint_as_float(v[c4 * 4 + 0]), scale, b4.x));
+            const float m1 = silu(fmaf(__uint_as_float(v[c4 * 4 + 1]), scale, b4.y));
+            const float m2 = silu(fmaf(__uint_as_float(v[c4 * 4 + 2]), scale, b4.z));
+            const float m3 = silu(fmaf(__uint_as_float(v[c4 * 4 + 3]), scale, b4.w));
+            dot = fmaf(w4.x, m0, dot); dot = fmaf(w4.y, m1, dot); dot = fmaf(w4.z, m2, dot); dot = fmaf(w4.w, m3, dot);
+            v[c4 * 4 + 0] = __float_as_uint(m0); v[c4 * 4 + 1] = __float_as_uint(m1);
+            v[c4 * 4 + 2] = __float_as_uint(m2); v[c4 * 4 + 3] = __float_as_uint(m3);
+          }
+          if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
+        }
+        s_dot[hf * TM + r] = dot;
+        if (MODE == MODE_GCL) tmem_st_wait();
+        named_bar_sync(2 + (warp & 3), 64);
+        const float full_dot = s_dot[r] + s_dot[TM + r];
+        const int prev_i = __shfl_up_sync(0xffffffffu, my_i, 1);
+        const bool head = valid && (lane == 0 || prev_i != my_i);
+        const unsigned hm = __ballot_sync(0xffffffffu, head);
+        const int nval = __popc(__ballot_sync(0xffffffffu, valid));
+        const int npiece = __popc(hm);
+        if (MODE == MODE_EQUIV) {
+          tc_fence_before();
+          release_acc(region);
+          if (hf == 0) {
+            float phi = a.use_tanh ? tanhf(full_dot) : full_dot;
+            float dx = __fmul_rn(ux, phi), dy = __fmul_rn(uy, phi), dz = __fmul_rn(uz, phi);
+            if (a.use_tanh) { dx = __fmul_rn(dx, a.coords_range); dy = __fmul_rn(dy, a.coords_range); dz = __fmul_rn(dz, a.coords_range); }
+            s_dx[4 * r] = valid ? dx : 0.f; s_dx[4 * r + 1] = valid ? dy : 0.f; s_dx[4 * r + 2] = valid ? dz : 0.f;
+            __syncwarp();
+            if (head) {
+              const unsigned after = hm & ~((2u << lane) - 1u);
+              const int q1 = after ? (__ffs(after) - 1) : nval;
+              float sx = 0.f, sy = 0.f, sz = 0.f;
+              for (int q = lane; q < q1; ++q) {
+                const float* d = s_dx + 4 * ((warp & 3) * 32 + q);
+                sx += d[0]; sy += d[1]; sz += d[2];
+              }
+              atomicAdd(a.out + (size_t)my_i * 3, sx);
+              atomicAdd(a.out + (size_t)my_i * 3 + 1, sy);
+              atomicAdd(a.out + (size_t)my_i * 3 + 2, sz);
+            }
+            __syncwarp();
+          }
+          named_bar_sync(2 + (warp & 3), 64);
+        } else {
+          float g = a.attention ? sigmoidf_(full_dot + __ldg(a.b_out)) : 1.0f;
+          if (!valid) g = 0.f;
+          float* Tw = reinterpret_cast<float*>(smem + S::OFF_T) + warp * (32 * 36);
+          int* psw = s_ps + warp * 34;
+          if (head) psw[__popc(hm & ((1u << lane) - 1u))] = lane;
+          if (lane == 0) psw[npiece] = nval;
+          __syncwarp();
+#pragma unroll 1
+          for (int cc = 0; cc < NCH; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            tmem_ld_wait();
+            if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
+                                      __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
+              *reinterpret_cast<float4*>(Tw + lane * 36 + c4 * 4) = e4;
+            }
+            __syncwarp();
+            for (int pc = 0; pc < npiece; ++pc) {
+              const int q0 = psw[pc], q1 = psw[pc + 1];
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              const float* tp = Tw + q0 * 36 + lane;
+              int q = q0;
+              for (; q + 4 <= q1; q += 4, tp += 4 * 36) {
+                s0 += tp[0];
+                s1 += tp[36];
+                s2 += tp[72];
+                s3 += tp[108];
+              }
+              for (; q < q1; ++q, tp += 36) s0 += tp[0];
+              const int pi = s_i[(warp & 3) * 32 + q0];
+              atomicAdd(a.out + (size_t)pi * H + hf * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
+            }
+            __syncwarp();
+          }
+          named_bar_sync(2 + (warp & 3), 64);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+template <int H, int MODE>
+int launch_mode(const Args& a, cudaStream_t st) {
+  using S = Smem<H, MODE>;
+  static int sm_count = 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc16_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
+    if (e != cudaSuccess) {
+      set_error("tc16_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
+      return -2;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  if (a.n_tile == 0) return 0;
+  const int work = (a.n_tile + 1) / 2 * 2 * a.n_blocks;
+  int grid = work < sm_count ? work : sm_count;
+  grid = grid / 2 * 2;
+  Args args = a;
+  args.rz_scale = 1.0f + RZ_BIAS_PER_MMA * (float)(a.n_slabs * (BK / 16) * 3);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = S::ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc16_kernel<H, MODE>, args);
+  if (e != cudaSuccess) {
+    set_error("tc16_kernel launch: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+template <int MODE>
+int launch_h(int H, const Args& a, cudaStream_t st) {
+  switch (H) {
+    case 64: return launch_mode<64, MODE>(a, st);
+    case 128: return launch_mode<128, MODE>(a, st);
+    case 192: return launch_mode<192, MODE>(a, st);
+    case 256: return launch_mode<256, MODE>(a, st);
+    default: set_error("tcgen05 kernels support hidden_nf 64/128/192/256, got %d", H); return -1;
+  }
+}
+
+// fp16 split of the scaled weights, one thread per element: W[n][k] -> block n/H, slab k/64, N-half, hi|lo images
+__global__ void pack16_amax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like uints
+}
+
+__global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int k, uint8_t* __restrict__ pack) {
+  // scale 2^e with max|w| 2^e in [2^13, 2^14)  (zero matrix: e = 0)
+  const float amax = __uint_as_float(*reinterpret_cast<const unsigned*>(pack + 4));
+  int e = 0;
+  if (amax > 0.f) { int ex; frexpf(amax, &ex); e = 14 - ex; }       // amax = f * 2^ex, f in [0.5, 1)
+  e = max(-100, min(100, e));
+  const float scale = ldexpf(1.0f, e);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *reinterpret_cast<float*>(pack) = ldexpf(1.0f, -e);
+  if (idx >= (size_t)n_out * k) return;
+  const int n = (int)(idx / k), kk = (int)(idx % k);
+  const int nb = n / H, nl = n % H, slab = kk / 64, kl = kk % 64;
+  const int n_slabs = k / 64;
+  const float v = w[idx] * scale;                                   // exact (power of two)
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const int NH = H / 2, half = nl / NH, rl = nl % NH;
+  // (row rl, 16-byte chunk kl/8) of a SWIZZLE_128B K-major image with 128-byte rows, element index inside the chunk kl%8
+  const size_t off = (size_t)(rl >> 3) * 1024 + (rl & 7) * 128 + ((((kl >> 3) ^ (rl & 7)) << 4) | ((kl & 7) << 1));
+  uint8_t* img = pack + PACK_HDR + (size_t)((nb * n_slabs + slab) * 2 + half) * 2 * (size_t)NH * 128;
+  *reinterpret_cast<__half*>(img + off) = hi;
+  *reinterpret_cast<__half*>(img + (size_t)NH * 128 + off) = lo;
+}
+}  // namespace
+
+int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
+                     const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
+  GEOLDM_REQUIRE(b.tile_m == TM, "edge_tc16: batch tile_m=%d, kernel needs %d", b.tile_m, TM);
+  GEOLDM_REQUIRE(w.tc_pack != nullptr, "edge_tc16: tc_pack missing (weights not packed for the tensor-core path)");
+  GEOLDM_REQUIRE(equiv || !cfg.attention || w.b_out != nullptr, "edge_tc16: attention needs b_out");
+  GEOLDM_REQUIRE(cfg.hidden_nf % BK == 0, "edge_tc16: hidden_nf %d must be a multiple of %d", cfg.hidden_nf, BK);
+  Args a{};
+  a.n_tile = b.n_tile; a.n_rows = b.n_edge; a.tile_row = b.tile_row; a.n_blocks = 1;
+  a.n_slabs = cfg.hidden_nf / BK;
+  a.pq = pq; a.pq_ld = pq_ld; a.x = x; a.x0 = x0; a.edge_i = b.edge_i; a.edge_j = b.edge_j; a.w_rd = w.w_rd;
+  a.w_pack = reinterpret_cast<const uint8_t*>(w.tc_pack);
+  a.b2 = w.b2; a.w_out = w.w_out; a.b_out = w.b_out; a.out = out;
+  a.norm_constant = cfg.norm_constant; a.coords_range = cfg.coords_range;
+  a.attention = cfg.attention; a.use_tanh = cfg.tanh;
+  return equiv ? launch_h<MODE_EQUIV>(cfg.hidden_nf, a, st) : launch_h<MODE_GCL>(cfg.hidden_nf, a, st);
+}
+
+int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
+                       int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st) {
+  GEOLDM_REQUIRE(k1 % BK == 0 && k2 % BK == 0 && k1 + k2 > 0, "linear_tc16: k1=%d k2=%d must be multiples of %d", k1, k2, BK);
+  GEOLDM_REQUIRE(w_pack != nullptr, "linear_tc16: w_pack missing");
+  Args a{};
+  a.n_tile = (m + TM - 1) / TM; a.n_rows = m; a.tile_row = nullptr; a.n_blocks = n_blocks;
+  a.n_slabs = (k1 + k2) / BK;
+  a.a1 = a1; a.a2 = a2; a.k1 = k1; a.k2 = k2; a.a2_div = a2_div;
+  a.w_pack = reinterpret_cast<const uint8_t*>(w_pack);
+  a.b2 = bias; a.res = res; a.epi = epi; a.out = out; a.ldo = n_blocks * H;
+  return launch_h<MODE_DENSE>(H, a, st);
+}
+
+int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,
+                         const void* w_pack, float* out, cudaStream_t st) {
+  Args a{};
+  a.n_tile = n_tile; a.n_rows = n_rows; a.tile_row = tile_row; a.n_blocks = 1; a.n_slabs = H / BK;
+  a.pq = pq; a.pq_ld = 2 * H; a.edge_i = edge_i; a.w_pack = reinterpret_cast<const uint8_t*>(w_pack); a.out = out; a.ldo = H;
+  return launch_h<MODE_RAW>(H, a, st);
+}
+
+}  // namespace geoldm
+
+extern "C" {
+size_t geoldm_tc_pack16_bytes(int H, int n_out, int k) {
+  (void)H;
+  return geoldm::PACK_HDR + (size_t)n_out * k * 2 * sizeof(__half);
+}
+
+int geoldm_tc_pack16(int H, const float* w, int n_out, int k, void* pack, void* stream) {
+  GEOLDM_REQUIRE(H % 64 == 0 && H <= 256 && n_out % H == 0 && k % 64 == 0, "tc_pack16: H=%d n_out=%d k=%d", H, n_out, k);
+  const size_t tot = (size_t)n_out * k;
+  if (tot == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(pack, 0, geoldm::PACK_HDR, st);
+  if (e != cudaSuccess) { geoldm::set_error("tc_pack16: memset: %s", cudaGetErrorString(e)); return -2; }
+  unsigned* amax = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(pack) + 4);
+  geoldm::pack16_amax_kernel<<<(unsigned)((tot + 255) / 256 < 1024 ? (tot + 255) / 256 : 1024), 256, 0, st>>>(w, tot, amax);
+  GEOLDM_CHECK_LAUNCH("pack16_amax_kernel");
+  geoldm::pack16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(H, w, n_out, k, reinterpret_cast<uint8_t*>(pack));
+  GEOLDM_CHECK_LAUNCH("pack16_kernel");
+  return 0;
+}
+}

@@ -19,7 +19,8 @@ from torch import nn
 from . import _lib
 from .packing import RaggedBatch
 
-TILE_M = {_lib.MMA_FP32_SIMT: 64, _lib.MMA_3XTF32: 128, _lib.MMA_TF32: 128, _lib.MMA_BF16: 128}
+TILE_M = {_lib.MMA_FP32_SIMT: 64, _lib.MMA_3XTF32: 128, _lib.MMA_TF32: 128, _lib.MMA_BF16: 128,
+          _lib.MMA_3XF16: 128}
 
 
 def _require_silu(act_fn):
@@ -167,8 +168,12 @@ class EGNN(nn.Module):
                 return None
             wmat = wmat.detach().to(torch.float32).contiguous()
             n_out, k = wmat.shape
-            buf = torch.empty(L.geoldm_tc_pack_bytes(H, n_out, k), dtype=torch.uint8, device=wmat.device)
-            _lib.check(L.geoldm_tc_pack(H, _lib.ptr(wmat), n_out, k, _lib.ptr(buf), stream), "geoldm_tc_pack")
+            if mode == _lib.MMA_3XF16:
+                buf = torch.empty(L.geoldm_tc_pack16_bytes(H, n_out, k), dtype=torch.uint8, device=wmat.device)
+                _lib.check(L.geoldm_tc_pack16(H, _lib.ptr(wmat), n_out, k, _lib.ptr(buf), stream), "geoldm_tc_pack16")
+            else:
+                buf = torch.empty(L.geoldm_tc_pack_bytes(H, n_out, k), dtype=torch.uint8, device=wmat.device)
+                _lib.check(L.geoldm_tc_pack(H, _lib.ptr(wmat), n_out, k, _lib.ptr(buf), stream), "geoldm_tc_pack")
             keep.append(wmat)
             keep.append(buf)
             return buf.data_ptr()

@@ -35,7 +35,10 @@ enum {
   GEOLDM_MMA_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores (exact fp32 products)               */
   GEOLDM_MMA_3XTF32 = 1,      /* tcgen05 kind::tf32, hi*hi + hi*lo + lo*hi, fp32 accumulate  */
   GEOLDM_MMA_TF32 = 2,        /* tcgen05 kind::tf32 single pass (fast mode, fails 1e-5 gate) */
-  GEOLDM_MMA_BF16 = 3         /* tcgen05 kind::f16 bf16 single pass (fast mode)              */
+  GEOLDM_MMA_BF16 = 3,        /* tcgen05 kind::f16 bf16 single pass (not implemented)        */
+  GEOLDM_MMA_3XF16 = 4        /* tcgen05 kind::f16, fp16 hi/lo split of both operands (3 products, fp32 accumulate):
+                                 same 22-bit products as 3xTF32 at twice the MMA rate; needs |activation| < 65504;
+                                 weight images from geoldm_tc_pack16                          */
 };
 
 /* Mirrors the ctor kwargs of EGNN / EGNN_dynamics_QM9 (egnn/egnn_new.py:151-153, egnn/models.py:9-13). */
@@ -169,7 +172,13 @@ int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div
  * SWIZZLE_128B K-major order (the exact bytes the TMA engine drops into shared memory).  Runs on `stream`. */
 size_t geoldm_tc_pack_bytes(int H, int n_out, int k);
 int geoldm_tc_pack(int H, const float* w, int n_out, int k, void* pack, void* stream);
-/* same contract as geoldm_linear with n = n_blocks*H outputs, on the tensor cores; terms: 3 = 3xTF32, 1 = TF32 */
+/* fp16-split pack for GEOLDM_MMA_3XF16: 128-byte header {float 2^-e, ...} followed by n_out/H column blocks x k/64
+ * k-slabs x 2 N-halves x {fp16-hi, fp16-lo} images of W * 2^e (e chosen on the device so that max|W| 2^e is in
+ * [2^13, 2^14)), same SWIZZLE_128B K-major order.  H and k multiples of 64. */
+size_t geoldm_tc_pack16_bytes(int H, int n_out, int k);
+int geoldm_tc_pack16(int H, const float* w, int n_out, int k, void* pack, void* stream);
+/* same contract as geoldm_linear with n = n_blocks*H outputs, on the tensor cores; terms: 3 = 3xTF32, 1 = TF32,
+ * 16 = 3xF16 (w_pack from geoldm_tc_pack16) */
 int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
                      const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out,
                      int m, void* stream);
