@@ -29,10 +29,22 @@ void set_error(const char* fmt, ...);
 // ---- math -----------------------------------------------------------------------------------
 // SiLU(v) = v / (1 + exp(-v)).  ex2.approx + fast divide: ~2-3 ulp, unbiased; the reference's CPU
 // path uses a 1-ulp vectorised expf, so both sit at the fp32 noise floor.
-__device__ __forceinline__ float silu(float v) {
-  return __fdividef(v, 1.0f + __expf(-v));
+// ex2 / rcp with flush-to-zero: the non-ftz forms add a range check and two predicated multiplies per call to return
+// denormal results, which 1 + exp(-v) then rounds away anyway.
+__device__ __forceinline__ float ex2_ftz(float v) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+  return y;
 }
-__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float rcp_ftz(float v) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+  return y;
+}
+__device__ __forceinline__ float silu(float v) {
+  return v * rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f));
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
 
   auto tile_of = [&](int iter, int& tile, int& nb, int& row0, int& nrows) {
     const int work = iter * n_workers + worker;
@@ -278,8 +279,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           }
         }
         bool waited = false;
-        uint8_t* a_hi = smem + S::OFF_A + st * S::A_STAGE;
-        uint8_t* a_lo = a_hi + TM * 128;
+        const uint32_t a_hi = sbase + S::OFF_A + st * S::A_STAGE;
+        const uint32_t a_lo = a_hi + TM * 128;
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {          // two rows at a time: bounds the registers held by loads in flight
           float4 v[2][2], q[2][2];
@@ -316,10 +317,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             float e[8];
             if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
+              for (int c = 0; c < 8; ++c)      // rows beyond the tile: v = q = 0, rr = dd = 0 -> SiLU(0) = 0 exactly
                 e[c] = silu(fmaf(wd[c], dd[p], fmaf(wr[c], rr[p], vv[c] + qq[c])));
-                if (!valid[p]) e[c] = 0.f;
-              }
             } else if (MODE == MODE_DENSE) {
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
@@ -333,8 +332,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             uint4 hi, lo;
             split_f16x8(e, hi, lo);
             const uint32_t off = sw128_off(r, chunk);
-            *reinterpret_cast<uint4*>(a_hi + off) = hi;
-            *reinterpret_cast<uint4*>(a_lo + off) = lo;
+            sts128(a_hi + off, hi);
+            sts128(a_lo + off, lo);
           }
         }
         fence_proxy_async_smem();
@@ -348,12 +347,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
     const int hf = warp >> 2;
     constexpr int HC = H / 2;
     constexpr int NCH = HC / 32;
-    int* s_i = reinterpret_cast<int*>(smem + S::OFF_SI);
-    int* s_ps = reinterpret_cast<int*>(smem + S::OFF_PS);
-    float* s_dx = reinterpret_cast<float*>(smem + S::OFF_DX);
-    float* s_dot = reinterpret_cast<float*>(smem + S::OFF_DOT);
-    const float* s_b2 = reinterpret_cast<const float*>(smem + S::OFF_VEC) + hf * HC;
-    const float* s_wo = s_b2 + H;
+    const uint32_t s_i = sbase + S::OFF_SI;          // int   [128] receiver per row
+    const uint32_t s_dx = sbase + S::OFF_DX;         // float [128][4]
+    const uint32_t s_dot = sbase + S::OFF_DOT;       // float [2][128]
+    const uint32_t s_b2 = sbase + S::OFF_VEC + hf * HC * 4;
+    const uint32_t s_wo = s_b2 + H * 4;
     const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * HC;
     // 2^-e of the weight images times the round-toward-zero compensation
     const float scale = __ldg(reinterpret_cast<const float*>(a.w_pack)) * a.rz_scale;
@@ -376,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             ux = g.ux; uy = g.uy; uz = g.uz;
           }
         }
-        if (hf == 0) s_i[r] = my_i;
+        if (hf == 0) sts32i(s_i + 4 * r, my_i);
       }
       mbar_wait(&acc_full[region], (iter >> 1) & 1);
       tc_fence_after();
@@ -420,8 +418,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           tmem_ld_wait();
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_b2 + cc * 32 + c4 * 4);
-            const float4 w4 = *reinterpret_cast<const float4*>(s_wo + cc * 32 + c4 * 4);
+            const float4 b4 = lds128f(s_b2 + (cc * 32 + c4 * 4) * 4);
+            const float4 w4 = lds128f(s_wo + (cc * 32 + c4 * 4) * 4);
             const float m0 = silu(fmaf(__uint_as_float(v[c4 * 4 + 0]), scale, b4.x));
             const float m1 = silu(fmaf(__uint_as_float(v[c4 * 4 + 1]), scale, b4.y));
             const float m2 = silu(fmaf(__uint_as_float(v[c4 * 4 + 2]), scale, b4.z));
@@ -432,10 +430,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           }
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
         }
-        s_dot[hf * TM + r] = dot;
+        sts32f(s_dot + (hf * TM + r) * 4, dot);
         if (MODE == MODE_GCL) tmem_st_wait();
         named_bar_sync(2 + (warp & 3), 64);
-        const float full_dot = s_dot[r] + s_dot[TM + r];
+        const float full_dot = lds32f(s_dot + r * 4) + lds32f(s_dot + (TM + r) * 4);
         const int prev_i = __shfl_up_sync(0xffffffffu, my_i, 1);
         const bool head = valid && (lane == 0 || prev_i != my_i);
         const unsigned hm = __ballot_sync(0xffffffffu, head);
@@ -448,15 +446,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             float phi = a.use_tanh ? tanhf(full_dot) : full_dot;
             float dx = __fmul_rn(ux, phi), dy = __fmul_rn(uy, phi), dz = __fmul_rn(uz, phi);
             if (a.use_tanh) { dx = __fmul_rn(dx, a.coords_range); dy = __fmul_rn(dy, a.coords_range); dz = __fmul_rn(dz, a.coords_range); }
-            s_dx[4 * r] = valid ? dx : 0.f; s_dx[4 * r + 1] = valid ? dy : 0.f; s_dx[4 * r + 2] = valid ? dz : 0.f;
+            sts128f(s_dx + 16 * r, make_float4(valid ? dx : 0.f, valid ? dy : 0.f, valid ? dz : 0.f, 0.f));
             __syncwarp();
             if (head) {
               const unsigned after = hm & ~((2u << lane) - 1u);
               const int q1 = after ? (__ffs(after) - 1) : nval;
               float sx = 0.f, sy = 0.f, sz = 0.f;
               for (int q = lane; q < q1; ++q) {
-                const float* d = s_dx + 4 * ((warp & 3) * 32 + q);
-                sx += d[0]; sy += d[1]; sz += d[2];
+                const float4 d = lds128f(s_dx + 16 * ((warp & 3) * 32 + q));
+                sx += d.x; sy += d.y; sz += d.z;
               }
               atomicAdd(a.out + (size_t)my_i * 3, sx);
               atomicAdd(a.out + (size_t)my_i * 3 + 1, sy);
@@ -468,10 +466,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
         } else {
           float g = a.attention ? sigmoidf_(full_dot + __ldg(a.b_out)) : 1.0f;
           if (!valid) g = 0.f;
-          float* Tw = reinterpret_cast<float*>(smem + S::OFF_T) + warp * (32 * 36);
-          int* psw = s_ps + warp * 34;
-          if (head) psw[__popc(hm & ((1u << lane) - 1u))] = lane;
-          if (lane == 0) psw[npiece] = nval;
+          const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);     // this warp's [32][36] fp32 transposition tile
+          const uint32_t psw = sbase + S::OFF_PS + warp * (34 * 4);       // this warp's piece starts (+ end sentinel)
+          if (head) sts32i(psw + 4 * __popc(hm & ((1u << lane) - 1u)), lane);
+          if (lane == 0) sts32i(psw + 4 * npiece, nval);
           __syncwarp();
 #pragma unroll 1
           for (int cc = 0; cc < NCH; ++cc) {
@@ -483,22 +481,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             for (int c4 = 0; c4 < 8; ++c4) {
               float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
                                       __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
-              *reinterpret_cast<float4*>(Tw + lane * 36 + c4 * 4) = e4;
+              sts128f(Tw + (lane * 36 + c4 * 4) * 4, e4);
             }
             __syncwarp();
             for (int pc = 0; pc < npiece; ++pc) {
-              const int q0 = psw[pc], q1 = psw[pc + 1];
+              const int q0 = lds32i(psw + 4 * pc), q1 = lds32i(psw + 4 * pc + 4);
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-              const float* tp = Tw + q0 * 36 + lane;
+              uint32_t tp = Tw + (q0 * 36 + lane) * 4;
               int q = q0;
-              for (; q + 4 <= q1; q += 4, tp += 4 * 36) {
-                s0 += tp[0];
-                s1 += tp[36];
-                s2 += tp[72];
-                s3 += tp[108];
+              for (; q + 4 <= q1; q += 4, tp += 4 * 36 * 4) {
+                s0 += lds32f(tp);
+                s1 += lds32f(tp + 36 * 4);
+                s2 += lds32f(tp + 72 * 4);
+                s3 += lds32f(tp + 108 * 4);
               }
-              for (; q < q1; ++q, tp += 36) s0 += tp[0];
-              const int pi = s_i[(warp & 3) * 32 + q0];
+              for (; q < q1; ++q, tp += 36 * 4) s0 += lds32f(tp);
+              const int pi = lds32i(s_i + 4 * ((warp & 3) * 32 + q0));
               atomicAdd(a.out + (size_t)pi * H + hf * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
             }
             __syncwarp();
