@@ -217,7 +217,7 @@ def main():
     L = _lib.lib()
     mode = args.mma_mode
     if mode == "auto":
-        mode = "3xtf32" if L.geoldm_has_tcgen05() else "fp32"
+        mode = "3xf16" if L.geoldm_has_tcgen05() else "fp32"
     margs = qm9_args(mode)
     info = {"atom_decoder": ["H", "C", "N", "O", "F"], "n_nodes": {5: 1}, "max_n_nodes": 29}
     torch.manual_seed(0)

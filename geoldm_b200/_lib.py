@@ -75,6 +75,7 @@ _SIGS = {
     "geoldm_gemm_tn": (C.c_int, [fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
     "geoldm_stability": (C.c_int, [C.c_int, fp, fp, fp, C.c_int, fp, fp, C.c_int, fp, fp, fp]),
     "geoldm_tc_read_stats": (C.c_int, [C.POINTER(C.c_ulonglong)]),
+    "geoldm_tc16_read_stats": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "geoldm_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, fp, C.c_int, fp]),
     "geoldm_decode": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp]),
 }

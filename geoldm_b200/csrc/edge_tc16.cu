@@ -17,7 +17,18 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifdef GEOLDM_TC_PROFILE
+#define TC_PROF(...) __VA_ARGS__
+#else
+#define TC_PROF(...)
+#endif
+
 namespace geoldm {
+// cycle counters of one MMA / producer / epilogue thread of CTA 0 (GEOLDM_TC_PROFILE builds only):
+// [0] MMA total [1] wait acc_empty [2] wait a_full [3] wait w [4] launches [5] tiles
+// [6] producer wait a_empty (+loads) [7] producer compute+store [8] producer fence+arrive [9] producer metadata
+// [10] epilogue wait acc_full [11] pass 1 [12] barrier + gate [13] pass 2 [14] epilogue metadata
+__device__ unsigned long long g_tc16_stats[16];
 namespace {
 using namespace tc;
 
@@ -189,16 +200,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
     if (crank == 0) {
       const uint32_t idesc = make_idesc_f16_m256(H);
       uint32_t wit = 0, ait = 0;
+      TC_PROF(long long t_acc = 0; long long t_a = 0; long long t_w = 0; const long long t_begin = clock64();)
       for (int iter = 0; iter < n_iter; ++iter) {
         const int region = iter & 1;
+        TC_PROF(long long t0 = clock64();)
         mbar_wait_cluster(&acc_empty[region], ((iter >> 1) & 1) ^ 1);
+        TC_PROF(t_acc += clock64() - t0;)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + region * 256;
         for (int s = 0; s < a.n_slabs; ++s, ++ait, ++wit) {
           const int ast = ait % NAS, wst = wit % NWS;
+          TC_PROF(t0 = clock64();)
           mbar_wait_cluster(&a_full[ast], (ait / NAS) & 1);
+          TC_PROF(long long t1 = clock64();)
           mbar_wait(&w_full[wst], (wit / NWS) & 1);
           mbar_wait_cluster(&w_peer[wst], (wit / NWS) & 1);
+          TC_PROF(t_a += t1 - t0; t_w += clock64() - t1;)
           tc_fence_after();
           if (lane == 0) {
             const uint32_t a_hi = smem_u32(smem + S::OFF_A + ast * S::A_STAGE);
@@ -220,6 +237,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           __syncwarp();
         }
       }
+      TC_PROF(if (lane == 0 && blockIdx.x == 0) {
+        g_tc16_stats[0] += (unsigned long long)(clock64() - t_begin);
+        g_tc16_stats[1] += (unsigned long long)t_acc;
+        g_tc16_stats[2] += (unsigned long long)t_a;
+        g_tc16_stats[3] += (unsigned long long)t_w;
+        g_tc16_stats[4] += 1ull;
+        g_tc16_stats[5] += (unsigned long long)n_iter;
+      })
     }
   } else if (warp >= 8) {
     // =========================== A producers (256 threads) ================================================
@@ -227,7 +252,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
     const int chunk = pt & 7;        // 16-byte chunk: k = 8*chunk .. 8*chunk+7 inside the slab
     const int rbase = pt >> 3;       // rows rbase + 32 p
     uint32_t it = 0;
+    TC_PROF(long long tp_wait = 0; long long tp_comp = 0; long long tp_fence = 0; long long tp_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
+      TC_PROF(const long long tm0 = clock64();)
       int tile, nb, row0, nrows;
       tile_of(iter, tile, nb, row0, nrows);
       const float* pP[4];
@@ -261,9 +288,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           }
         }
       }
+      TC_PROF(tp_meta += clock64() - tm0;)
       for (int s = 0; s < a.n_slabs; ++s, ++it) {
         const int st = it % NAS;
         const int k0 = s * BK;
+        TC_PROF(const long long tp0 = clock64(); long long tp1 = tp0;)
         float wr[8], wd[8];
         if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 8 * chunk));
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
               }
             }
           }
-          if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; }
+          if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             const int p = 2 * ph + pp;
@@ -336,11 +365,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             sts128(a_lo + off, lo);
           }
         }
+        TC_PROF(const long long tp2 = clock64();)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) { if (crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+        TC_PROF(tp_wait += tp1 - tp0; tp_comp += tp2 - tp1; tp_fence += clock64() - tp2;)
       }
     }
+    TC_PROF(if (tid == EPI_T && blockIdx.x == 0) {
+      g_tc16_stats[6] += (unsigned long long)tp_wait; g_tc16_stats[7] += (unsigned long long)tp_comp;
+      g_tc16_stats[8] += (unsigned long long)tp_fence; g_tc16_stats[9] += (unsigned long long)tp_meta;
+    })
   } else {
     // ============= epilogue (warps 0-7: thread = (TMEM lane = row, column half)) ==========================
     const int r = (warp & 3) * 32 + lane;
@@ -359,7 +394,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
       __syncwarp();
       if (lane == 0) { if (crank != 0) mbar_arrive_remote(&acc_empty[region], 0); else mbar_arrive(&acc_empty[region]); }
     };
+    TC_PROF(long long te_wait = 0; long long te_p1 = 0; long long te_bar = 0; long long te_p2 = 0; long long te_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
+      TC_PROF(const long long te0 = clock64();)
       int tile, nb, row0, nrows;
       tile_of(iter, tile, nb, row0, nrows);
       const bool valid = r < nrows;
@@ -376,8 +413,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
         }
         if (hf == 0) sts32i(s_i + 4 * r, my_i);
       }
+      TC_PROF(const long long te1 = clock64();)
       mbar_wait(&acc_full[region], (iter >> 1) & 1);
       tc_fence_after();
+      TC_PROF(const long long te2 = clock64(); te_meta += te1 - te0; te_wait += te2 - te1;)
       const uint32_t taddr = tlane + region * 256;
 
       if (MODE == MODE_DENSE || MODE == MODE_RAW) {
@@ -430,6 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           }
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
         }
+        TC_PROF(const long long te3 = clock64(); te_p1 += te3 - te2;)
         sts32f(s_dot + (hf * TM + r) * 4, dot);
         if (MODE == MODE_GCL) tmem_st_wait();
         named_bar_sync(2 + (warp & 3), 64);
@@ -466,6 +506,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
         } else {
           float g = a.attention ? sigmoidf_(full_dot + __ldg(a.b_out)) : 1.0f;
           if (!valid) g = 0.f;
+          TC_PROF(const long long te4 = clock64(); te_bar += te4 - te3;)
           const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);     // this warp's [32][36] fp32 transposition tile
           const uint32_t psw = sbase + S::OFF_PS + warp * (34 * 4);       // this warp's piece starts (+ end sentinel)
           if (head) sts32i(psw + 4 * __popc(hm & ((1u << lane) - 1u)), lane);
@@ -501,10 +542,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             }
             __syncwarp();
           }
+          TC_PROF(te_p2 += clock64() - te4;)
           named_bar_sync(2 + (warp & 3), 64);
         }
       }
     }
+    TC_PROF(if (tid == 0 && blockIdx.x == 0) {
+      g_tc16_stats[10] += (unsigned long long)te_wait; g_tc16_stats[11] += (unsigned long long)te_p1;
+      g_tc16_stats[12] += (unsigned long long)te_bar; g_tc16_stats[13] += (unsigned long long)te_p2;
+      g_tc16_stats[14] += (unsigned long long)te_meta;
+    })
   }
 
   tc_fence_before();
@@ -645,6 +692,14 @@ int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* t
 }  // namespace geoldm
 
 extern "C" {
+/* debug (GEOLDM_TC_PROFILE builds): read + reset the 16 cycle counters of the fp16-split kernel; synchronises */
+int geoldm_tc16_read_stats(unsigned long long* host_out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_out, geoldm::g_tc16_stats, sizeof(unsigned long long) * 16);
+  unsigned long long zero[16] = {0};
+  cudaMemcpyToSymbol(geoldm::g_tc16_stats, zero, sizeof(zero));
+  return 0;
+}
 size_t geoldm_tc_pack16_bytes(int H, int n_out, int k) {
   (void)H;
   return geoldm::PACK_HDR + (size_t)n_out * k * 2 * sizeof(__half);

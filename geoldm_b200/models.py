@@ -1,7 +1,7 @@
 """Model factory with the reference's surface (qm9/models.py): ``get_latent_diffusion(args, device,
 dataset_info, dataloader_train) -> (model, nodes_dist, prop_dist)`` (:103-166), ``get_autoencoder`` (:54-100)
 and ``DistributionNodes`` (:178-215).  ``args`` is the same argparse Namespace the reference uses; the extra
-optional attribute ``args.mma_mode`` ("fp32" | "3xtf32" | "tf32" | "bf16") selects the arithmetic of the
+optional attribute ``args.mma_mode`` ("fp32" | "3xf16" | "3xtf32" | "tf32") selects the arithmetic of the
 fused kernels."""
 from __future__ import annotations
 

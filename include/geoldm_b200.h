@@ -201,6 +201,8 @@ int geoldm_stability(int n_mol, const int* mol_off, const float* x, const int* a
 /* debug (GEOLDM_TC_DEBUG & 32): read+reset cycle counters of the MMA-issuing thread of CTA 0:
  * {total, wait acc_empty, wait a_full, wait w_full, launches, tiles, 0, 0}; synchronises the device */
 int geoldm_tc_read_stats(unsigned long long* host_out);
+/* same for the fp16-split kernels (16 counters: MMA thread, one producer thread, one epilogue thread of CTA 0) */
+int geoldm_tc16_read_stats(unsigned long long* host_out);
 /* Philox4x32-10 standard normals (Box-Muller), the sampler's noise stream exposed for tests:
  * out[4*d+e] = e-th normal of block counter=(d, node, blk, seed>>32), key=(mol_id, (uint32)seed), i.e. what
  * geoldm_sampler_update draws for draw index d, node `node` of molecule `mol_id`, columns 4*blk+e. */

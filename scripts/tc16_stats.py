@@ -1,0 +1,40 @@
+"""GEOLDM_TC_PROFILE=1 python -m geoldm_b200.build --force; python scripts/tc16_stats.py
+Cycle breakdown of the fp16-split edge kernels (MMA thread, one producer thread, one epilogue thread of CTA 0)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from geoldm_b200 import _lib
+from geoldm_b200.models import get_latent_diffusion
+from geoldm_b200.packing import pack_molecules
+L = _lib.lib()
+dev = torch.device("cuda:0")
+margs = bench.qm9_args("3xf16")
+info = {"atom_decoder": list("HCNOF"), "n_nodes": {5: 1}, "max_n_nodes": 29}
+torch.manual_seed(0)
+model, _, _ = get_latent_diffusion(margs, dev, info, None)
+bench.tame_(model, 256)
+nodes = bench.workload_nodes(1250)
+batch = pack_molecules(nodes, dev)
+dyn = model.dynamics
+w, _keep = dyn.egnn.packed()
+ccfg = dyn.egnn.c_config()
+cb = batch.c_batch(128)
+H = 256
+pq = torch.randn(batch.n_node, 2 * H, device=dev)
+xx = torch.randn(batch.n_node, 3, device=dev)
+out = (C.c_ulonglong * 16)()
+for name, fn, em, o in (("GCL", L.geoldm_edge_gcl, w.block[0].gcl[0].edge, torch.zeros(batch.n_node, H, device=dev)),
+                        ("EQUIV", L.geoldm_edge_equiv, w.block[0].equiv, torch.zeros(batch.n_node, 3, device=dev))):
+    for _ in range(3):
+        _lib.check(fn(C.byref(ccfg), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xx), _lib.ptr(xx), _lib.ptr(o), None), name)
+    L.geoldm_tc16_read_stats(out)
+    for _ in range(5):
+        _lib.check(fn(C.byref(ccfg), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xx), _lib.ptr(xx), _lib.ptr(o), None), name)
+    L.geoldm_tc16_read_stats(out)
+    v = [float(out[i]) for i in range(16)]
+    t = v[5]
+    print(f"{name}: per tile-pair cycles: MMA thread total {v[0]/t:.0f} | wait acc_empty {v[1]/t:.0f} | wait a_full {v[2]/t:.0f} | "
+          f"wait w {v[3]/t:.0f} | issue+other {(v[0]-v[1]-v[2]-v[3])/t:.0f}   ({v[4]:.0f} launches, {t/v[4]:.0f} tile-pairs per CTA)")
+    print(f"   producer thread: wait a_empty(+loads) {v[6]/t:.0f} | compute+store {v[7]/t:.0f} | fence+arrive {v[8]/t:.0f} | metadata {v[9]/t:.0f}")
+    print(f"   epilogue thread: wait acc_full {v[10]/t:.0f} | pass 1 {v[11]/t:.0f} | dot exchange+gate {v[12]/t:.0f} | pass 2 {v[13]/t:.0f} | metadata {v[14]/t:.0f}")

@@ -30,7 +30,7 @@ def make_args(nf, n_layers):
         sin_embedding=False, normalization_factor=1, aggregation_method="sum", kl_weight=0.01,
         normalize_factors=[1, 8, 1], condition_time=True, probabilistic_model="diffusion", diffusion_steps=1000,
         diffusion_noise_schedule="polynomial_2", diffusion_noise_precision=1e-5, diffusion_loss_type="l2",
-        trainable_ae=True, ema_decay=0.999, dataset="qm9_second_half", remove_h=False, mma_mode="3xtf32", lr=1e-4,
+        trainable_ae=True, ema_decay=0.999, dataset="qm9_second_half", remove_h=False, mma_mode="3xf16", lr=1e-4,
         clip_grad=True, ode_regularization=0.0)
 
 
