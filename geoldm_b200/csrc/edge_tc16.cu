@@ -289,7 +289,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
         }
       }
       TC_PROF(tp_meta += clock64() - tm0;)
-      for (int s = 0; s < a.n_slabs; ++s, ++it) {
+      // edge modes: K = H is a compile-time constant -> the slab loop is unrolled and every P/Q/w_rd load gets an
+      // immediate offset (no 64-bit address arithmetic per load)
+      constexpr int KS_STATIC = H / BK;
+      const int n_slabs_p = (MODE == MODE_DENSE) ? a.n_slabs : KS_STATIC;
+#pragma unroll(MODE == MODE_DENSE ? 1 : KS_STATIC)
+      for (int s = 0; s < n_slabs_p; ++s, ++it) {
         const int st = it % NAS;
         const int k0 = s * BK;
         TC_PROF(const long long tp0 = clock64(); long long tp1 = tp0;)
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           const float4 d1 = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 8 * chunk + 4));
           wr[0] = r0.x; wr[1] = r0.y; wr[2] = r0.z; wr[3] = r0.w; wr[4] = r1.x; wr[5] = r1.y; wr[6] = r1.z; wr[7] = r1.w;
           wd[0] = d0.x; wd[1] = d0.y; wd[2] = d0.z; wd[3] = d0.w; wd[4] = d1.x; wd[5] = d1.y; wd[6] = d1.z; wd[7] = d1.w;
-          if (s + 1 < a.n_slabs) {
+          if (s + 1 < n_slabs_p) {
 #pragma unroll
             for (int p = 0; p < 4; ++p)
               if (valid[p]) { prefetch_l1(pP[p] + k0 + BK); prefetch_l1(pQ[p] + k0 + BK); }
