@@ -371,6 +371,8 @@ def main():
             egnn_launches = 1 + Lb * (S * 4 + 3) + 1
         else:                   # equiv P|Q fused with the next block's gcl_0 P|Q
             egnn_launches = 1 + 1 + Lb * (S * 3 + (S - 1) + 3) + 1
+            if mode == "3xf16":  # per-edge squared distances: entry coordinates once, current coordinates per later block
+                egnn_launches += Lb
         launches_per_step = egnn_launches + 1 + 1 + 2 + 1 + 1   # + prep, nan-flag fill, finish a/b, update, advance
         line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

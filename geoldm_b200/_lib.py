@@ -51,7 +51,7 @@ _SIGS = {
     "geoldm_abi_version": (C.c_int, []),
     "geoldm_last_error": (C.c_char_p, []),
     "geoldm_has_tcgen05": (C.c_int, []),
-    "geoldm_egnn_workspace_bytes": (C.c_size_t, [C.POINTER(EgnnConfig), C.c_int]),
+    "geoldm_egnn_workspace_bytes": (C.c_size_t, [C.POINTER(EgnnConfig), C.c_int, C.c_int]),
     "geoldm_egnn_forward": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EgnnWeights), C.POINTER(Batch), fp, fp, fp, fp,
                                       fp, fp, C.c_size_t, fp]),
     "geoldm_dynamics_prep": (C.c_int, [C.POINTER(Batch), fp, fp, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp,
@@ -99,7 +99,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.geoldm_abi_version() != 1:
+        if handle.geoldm_abi_version() != 2:
             raise GeoldmError("ABI version mismatch between _lib.py and libgeoldm_b200.so")
         _lib = handle
     return _lib

@@ -17,9 +17,10 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct Workspace {
   float *h, *h2, *t1, *agg, *pq, *xa, *xb, *xagg, *dx;
+  float *r_edge, *d0_edge;   // [E] squared distances of the current / entry coordinates (tensor-core edge kernels)
   size_t bytes;
 };
-static Workspace carve(void* base, int n_node, int H) {
+static Workspace carve(void* base, int n_node, int n_edge, int H) {
   Workspace w;
   size_t off = 0;
   auto take = [&](size_t n_floats) {
@@ -30,16 +31,19 @@ static Workspace carve(void* base, int n_node, int H) {
   const size_t nh = (size_t)n_node * H;
   w.h = take(nh); w.h2 = take(nh); w.t1 = take(nh); w.agg = take(nh); w.pq = take(4 * nh);
   w.xa = take((size_t)3 * n_node); w.xb = take((size_t)3 * n_node); w.xagg = take((size_t)3 * n_node); w.dx = take((size_t)3 * n_node);
+  w.r_edge = take((size_t)n_edge); w.d0_edge = take((size_t)n_edge);
   w.bytes = off;
   return w;
 }
 
 static int edge_dispatch(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
-                         const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
+                         const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st,
+                         const float* r_edge = nullptr, const float* d0_edge = nullptr) {
   if (cfg.mma_mode == GEOLDM_MMA_FP32_SIMT) {
     GEOLDM_REQUIRE(pq_ld == 2 * cfg.hidden_nf, "edge_simt expects a [N][2H] projection buffer");
     return launch_edge_simt(cfg, w, b, equiv, pq, x, x0, out, st);
   }
+  if (cfg.mma_mode == GEOLDM_MMA_3XF16) return launch_edge_tc16(cfg, w, b, equiv, pq, pq_ld, x, x0, r_edge, d0_edge, out, st);
   return launch_edge_tc(cfg, w, b, equiv, pq, pq_ld, x, x0, out, st);
 }
 }  // namespace geoldm
@@ -51,8 +55,8 @@ extern "C" {
 int geoldm_abi_version(void) { return GEOLDM_ABI_VERSION; }
 const char* geoldm_last_error(void) { return g_err; }
 
-size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node) {
-  return carve(nullptr, n_node, cfg->hidden_nf).bytes;
+size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node, int n_edge) {
+  return carve(nullptr, n_node, n_edge, cfg->hidden_nf).bytes;
 }
 
 static int check_cfg(const geoldm_egnn_config* cfg) {
@@ -76,7 +80,7 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   const int terms = cfg->mma_mode == GEOLDM_MMA_TF32 ? 1 : cfg->mma_mode == GEOLDM_MMA_3XF16 ? 16 : 3;
   GEOLDM_REQUIRE(cfg->mma_mode != GEOLDM_MMA_BF16, "mma_mode bf16 is not implemented yet");
   if (N == 0) return 0;
-  Workspace ws = carve(workspace, N, H);
+  Workspace ws = carve(workspace, N, b->n_edge, H);
   GEOLDM_REQUIRE(workspace && workspace_bytes >= ws.bytes, "egnn_forward: workspace %zu < %zu bytes", workspace_bytes,
                  ws.bytes);
   int rc;
@@ -89,8 +93,17 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   // 4-column-block projection (equiv P|Q in columns [0,2H), next gcl_0 P|Q in [2H,4H))
   const float* pq_next = nullptr;
   int pq_next_ld = 2 * H;
+  // fp16-split kernels read the per-edge squared distances instead of recomputing them in every producer thread
+  const bool pre_dist = cfg->mma_mode == GEOLDM_MMA_3XF16;
+  const float* r_edge = pre_dist ? ws.r_edge : nullptr;
+  const float* d0_edge = pre_dist ? ws.d0_edge : nullptr;
+  if (pre_dist && (rc = launch_edge_dist(*b, x_in, ws.d0_edge, st))) return rc;
   for (int l = 0; l < cfg->n_layers; ++l) {
     const geoldm_block& blk = w->block[l];
+    if (pre_dist) {
+      if (l == 0) r_edge = ws.d0_edge;                    // x == x_in in the first block
+      else { if ((rc = launch_edge_dist(*b, x_cur, ws.r_edge, st))) return rc; r_edge = ws.r_edge; }
+    }
     for (int s = 0; s < cfg->inv_sublayers; ++s) {
       const geoldm_gcl& g = blk.gcl[s];
       const float* pq = ws.pq;
@@ -103,7 +116,7 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
         if ((rc = launch_linear(h, H, nullptr, 0, 1.f, g.edge.pq_wt, g.edge.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
       }
       cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
-      if ((rc = edge_dispatch(*cfg, g.edge, *b, false, pq, pq_ld, x_cur, x_in, ws.agg, st))) return rc;
+      if ((rc = edge_dispatch(*cfg, g.edge, *b, false, pq, pq_ld, x_cur, x_in, ws.agg, st, r_edge, d0_edge))) return rc;
       if (tcore) {
         if ((rc = launch_linear_tc(H, terms, h, H, ws.agg, H, cfg->agg_div, g.tc_pack_node1, 1, g.node_b1, nullptr, 1, ws.t1, N, st))) return rc;
         if ((rc = launch_linear_tc(H, terms, ws.t1, H, nullptr, 0, 1.f, g.tc_pack_node2, 1, g.node_b2, h, 2, h2, N, st))) return rc;
@@ -127,7 +140,7 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
       if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
     }
     cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
-    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, pq_ld, x_cur, x_in, ws.xagg, st))) return rc;
+    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, pq_ld, x_cur, x_in, ws.xagg, st, r_edge, d0_edge))) return rc;
     const bool last = (l + 1 == cfg->n_layers);
     float* x_next = last ? x_out : x_bufs[xi];
     float* dx_next = (last && dx_out) ? dx_out : ws.dx;   // dx is updated in place (elementwise)

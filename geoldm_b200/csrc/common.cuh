@@ -99,7 +99,10 @@ int launch_tc_selftest(int H, int terms, const float* pq, const int* edge_i, con
                        int n_rows, const void* w_pack, float* out, cudaStream_t st);
 // fp16-split variants (edge_tc16.cu), selected by terms == 16 / GEOLDM_MMA_3XF16
 int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
-                     const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st);
+                     const float* pq, int pq_ld, const float* x, const float* x0, const float* r_edge,
+                     const float* d0_edge, float* out, cudaStream_t st);
+// out[e] = |x_i - x_j|^2 for every packed edge (same association as edge_geom)
+int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, cudaStream_t st);
 int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
                        int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st);
 int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,

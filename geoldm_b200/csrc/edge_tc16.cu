@@ -51,6 +51,7 @@ struct Args {
   const float* x; const float* x0;
   const int* edge_i; const int* edge_j;
   const float* w_rd;
+  const float* r_edge; const float* d0_edge;   // [E] precomputed squared distances (or null: computed from x / x0)
   const float* a1; const float* a2; int k1, k2; float a2_div;
   const uint8_t* w_pack;    // header + [block][slab][N-half][hi image | lo image]
   const float* b2; const float* w_out; const float* b_out; const float* res;
@@ -276,6 +277,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             if (MODE != MODE_RAW) {
               const int j = a.edge_j[row0 + r];
               pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 8 * chunk;
+              if (a.r_edge) {
+                rr[p] = __ldg(a.r_edge + row0 + r);
+                dd[p] = __ldg(a.d0_edge + row0 + r);
+                continue;
+              }
               const float* xi = a.x + 3 * (size_t)i;
               const float* xj = a.x + 3 * (size_t)j;
               const float* yi = a.x0 + 3 * (size_t)i;
@@ -657,7 +663,8 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
 }  // namespace
 
 int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
-                     const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
+                     const float* pq, int pq_ld, const float* x, const float* x0, const float* r_edge,
+                     const float* d0_edge, float* out, cudaStream_t st) {
   GEOLDM_REQUIRE(b.tile_m == TM, "edge_tc16: batch tile_m=%d, kernel needs %d", b.tile_m, TM);
   GEOLDM_REQUIRE(w.tc_pack != nullptr, "edge_tc16: tc_pack missing (weights not packed for the tensor-core path)");
   GEOLDM_REQUIRE(equiv || !cfg.attention || w.b_out != nullptr, "edge_tc16: attention needs b_out");
@@ -666,6 +673,7 @@ int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, co
   a.n_tile = b.n_tile; a.n_rows = b.n_edge; a.tile_row = b.tile_row; a.n_blocks = 1;
   a.n_slabs = cfg.hidden_nf / BK;
   a.pq = pq; a.pq_ld = pq_ld; a.x = x; a.x0 = x0; a.edge_i = b.edge_i; a.edge_j = b.edge_j; a.w_rd = w.w_rd;
+  a.r_edge = (r_edge && d0_edge) ? r_edge : nullptr; a.d0_edge = d0_edge;
   a.w_pack = reinterpret_cast<const uint8_t*>(w.tc_pack);
   a.b2 = w.b2; a.w_out = w.w_out; a.b_out = w.b_out; a.out = out;
   a.norm_constant = cfg.norm_constant; a.coords_range = cfg.coords_range;

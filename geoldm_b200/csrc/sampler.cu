@@ -383,6 +383,21 @@ int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, co
   GEOLDM_CHECK_LAUNCH("outproj_kernel");
   return 0;
 }
+__global__ void edge_dist_kernel(int n_edge, const int* __restrict__ ei, const int* __restrict__ ej,
+                                 const float* __restrict__ x, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edge) return;
+  const float* xi = x + 3 * (size_t)ei[e];
+  const float* xj = x + 3 * (size_t)ej[e];
+  const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+  out[e] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, cudaStream_t st) {
+  if (b.n_edge == 0) return 0;
+  edge_dist_kernel<<<(b.n_edge + 255) / 256, 256, 0, st>>>(b.n_edge, b.edge_i, b.edge_j, x, out);
+  GEOLDM_CHECK_LAUNCH("edge_dist_kernel");
+  return 0;
+}
 int launch_coord_update(int n3, const float* x0, const float* dx, const float* xagg, float div, float* dx_next,
                         float* x_next, cudaStream_t st) {
   if (n3 == 0) return 0;

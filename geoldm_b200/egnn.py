@@ -235,9 +235,9 @@ class EGNN(nn.Module):
         mode = _lib.MMA_MODES[self.mma_mode] if isinstance(self.mma_mode, str) else int(self.mma_mode)
         return TILE_M[mode]
 
-    def workspace(self, n_node: int, device) -> torch.Tensor:
+    def workspace(self, n_node: int, device, n_edge: int = 0) -> torch.Tensor:
         cfg = self.c_config(1)
-        need = _lib.lib().geoldm_egnn_workspace_bytes(C.byref(cfg), n_node)
+        need = _lib.lib().geoldm_egnn_workspace_bytes(C.byref(cfg), n_node, n_edge)
         if self._ws is None or self._ws.numel() < need or self._ws.device != torch.device(device):
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
@@ -256,7 +256,7 @@ class EGNN(nn.Module):
         x_out = torch.empty(N, 3, device=h.device) if x_out is None else x_out
         w, _keep = self.packed()
         cfg = self.c_config(batch.n_max)
-        ws = self.workspace(N, h.device)
+        ws = self.workspace(N, h.device, batch.n_edge)
         cb = batch.c_batch(self.tile_m())
         st = torch.cuda.current_stream(h.device).cuda_stream
         _lib.check(_lib.lib().geoldm_egnn_forward(C.byref(cfg), C.byref(w), C.byref(cb), _lib.ptr(h), _lib.ptr(x),

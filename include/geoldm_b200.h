@@ -28,7 +28,7 @@ extern "C" {
 
 #define GEOLDM_MAX_LAYERS 16
 #define GEOLDM_MAX_SUBLAYERS 4
-#define GEOLDM_ABI_VERSION 1
+#define GEOLDM_ABI_VERSION 2
 
 /* arithmetic mode of the 256x256 edge/node contractions */
 enum {
@@ -114,7 +114,7 @@ const char* geoldm_last_error(void);
 int geoldm_has_tcgen05(void);
 
 /* ---- whole-network entry point: EGNN.forward (egnn/egnn_new.py:184-197) ------------------- */
-size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node);
+size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node, int n_edge);
 int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights* w, const geoldm_batch* b,
                         const float* h_in,  /* [N][in_node_nf] */
                         const float* x_in,  /* [N][3] */
