@@ -158,6 +158,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
+  // everything above touched only weights and on-chip state; results of the previous kernel are read from here on
+  pdl_launch_dependents();
+  pdl_wait_prior();
 
   auto tile_of = [&](int iter, int& tile, int& nb, int& row0, int& nrows) {
     const int work = iter * n_workers + worker;
@@ -601,13 +604,17 @@ int launch_mode(const Args& a, cudaStream_t st) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = S::ALLOC;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("GEOLDM_TC_PDL"); pdl = e ? atoi(e) : 1; }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc16_kernel<H, MODE>, args);
   if (e != cudaSuccess) {
     set_error("tc16_kernel launch: %s", cudaGetErrorString(e));

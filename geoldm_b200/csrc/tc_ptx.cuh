@@ -77,6 +77,11 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* g
       : "memory");
 }
 
+// ---- programmatic dependent launch: let the next kernel of the stream start its prologue while this one drains,
+// and wait for the previous kernel's results before touching them -------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- thread-block cluster ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
