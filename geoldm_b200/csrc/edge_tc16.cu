@@ -34,10 +34,22 @@ using namespace tc;
 
 constexpr int TM = 128;          // rows per tile (TMEM lanes)
 constexpr int BK = 64;           // k-slab: 64 fp16 = 128 bytes per row = one swizzle row
-constexpr int NTHREADS = 576;    // 8 epilogue + 8 producer warps + loader + MMA
 constexpr int NWS = 3;           // W pipeline stages
-constexpr int EPI_T = 256, PROD_T = 256;
-constexpr int WARP_LOAD = 16, WARP_MMA = 17;
+// Warp roles per mode.  The A generator is latency bound (two dependent global-load phases per k-slab and thread), so
+// the modes with a light fused tail (EQUIV, DENSE, RAW) run 16 producer warps (2 rows x 8 columns per thread and slab,
+// one load phase) and 4 epilogue warps (one per TMEM lane quarter, all H columns each); GCL keeps 8 + 8 because its
+// tail (second SiLU, gate, segment sum) is as long as its A generation.
+template <int MODE>
+struct Roles {
+  static constexpr int EPI_W = (MODE == 0) ? 8 : 4;
+  static constexpr int PROD_W = (MODE == 0) ? 8 : 16;
+  static constexpr int WARP_LOAD = EPI_W + PROD_W, WARP_MMA = WARP_LOAD + 1;
+  static constexpr int NTHREADS = 32 * (EPI_W + PROD_W + 2);
+  static constexpr int EPI_T = 32 * EPI_W;
+  static constexpr int ROW_STEP = 4 * PROD_W;                 // producer thread (rbase, chunk) owns rows rbase + ROW_STEP p
+  static constexpr int ROWS_PT = 128 / ROW_STEP;              // 4 or 2
+  static constexpr int NHALF = EPI_W / 4;                     // column halves split over distinct epilogue warps
+};
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
 constexpr uint32_t PACK_HDR = 128;   // bytes: float inv_scale at offset 0
 constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;   // see edge_tc.cu; re-measured for kind::f16 with scripts/tc_bias_probe.py
@@ -115,8 +127,11 @@ __device__ __forceinline__ void split_f16x8(const float (&e)[8], uint4& hi, uint
 }
 
 template <int H, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
+__global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Args a) {
   using S = Smem<H, MODE>;
+  using R = Roles<MODE>;
+  constexpr int NTHREADS = R::NTHREADS, EPI_T = R::EPI_T, WARP_LOAD = R::WARP_LOAD, WARP_MMA = R::WARP_MMA;
+  constexpr int ROWS_PT = R::ROWS_PT, ROW_STEP = R::ROW_STEP, NHALF = R::NHALF;
   constexpr int NAS = S::NAS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -143,8 +158,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
 
   if (tid == 0) {
     for (int s = 0; s < NWS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&w_peer[s], 1); }
-    for (int s = 0; s < NAS; ++s) { mbar_init(&a_full[s], 2 * PROD_T / 32); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * EPI_T / 32); }
+    for (int s = 0; s < NAS; ++s) { mbar_init(&a_full[s], 2 * R::PROD_W); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * R::EPI_W); }
     fence_barrier_init();
   }
   if (warp == WARP_MMA) tmem_alloc2(tmem_slot, 512);
@@ -250,24 +265,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
         g_tc16_stats[5] += (unsigned long long)n_iter;
       })
     }
-  } else if (warp >= 8) {
+  } else if (warp >= R::EPI_W) {
     // =========================== A producers (256 threads) ================================================
     const int pt = tid - EPI_T;
     const int chunk = pt & 7;        // 16-byte chunk: k = 8*chunk .. 8*chunk+7 inside the slab
-    const int rbase = pt >> 3;       // rows rbase + 32 p
+    const int rbase = pt >> 3;       // rows rbase + ROW_STEP p
     uint32_t it = 0;
     TC_PROF(long long tp_wait = 0; long long tp_comp = 0; long long tp_fence = 0; long long tp_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
       TC_PROF(const long long tm0 = clock64();)
       int tile, nb, row0, nrows;
       tile_of(iter, tile, nb, row0, nrows);
-      const float* pP[4];
-      const float* pQ[4];
-      float rr[4], dd[4];
-      bool valid[4];
+      const float* pP[ROWS_PT];
+      const float* pQ[ROWS_PT];
+      float rr[ROWS_PT], dd[ROWS_PT];
+      bool valid[ROWS_PT];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int r = rbase + 32 * p;
+      for (int p = 0; p < ROWS_PT; ++p) {
+        const int r = rbase + ROW_STEP * p;
         valid[p] = r < nrows;
         pP[p] = nullptr; pQ[p] = nullptr; rr[p] = 0.f; dd[p] = 0.f;
         if (valid[p]) {
@@ -317,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           wd[0] = d0.x; wd[1] = d0.y; wd[2] = d0.z; wd[3] = d0.w; wd[4] = d1.x; wd[5] = d1.y; wd[6] = d1.z; wd[7] = d1.w;
           if (s + 1 < n_slabs_p) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+            for (int p = 0; p < ROWS_PT; ++p)
               if (valid[p]) { prefetch_l1(pP[p] + k0 + BK); prefetch_l1(pQ[p] + k0 + BK); }
           }
         }
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
         const uint32_t a_hi = sbase + S::OFF_A + st * S::A_STAGE;
         const uint32_t a_lo = a_hi + TM * 128;
 #pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {          // two rows at a time: bounds the registers held by loads in flight
+        for (int ph = 0; ph < ROWS_PT / 2; ++ph) {   // two rows at a time: bounds the registers held by loads in flight
           float4 v[2][2], q[2][2];
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             const int p = 2 * ph + pp;
-            const int r = rbase + 32 * p;
+            const int r = rbase + ROW_STEP * p;
             const float vv[8] = {v[pp][0].x, v[pp][0].y, v[pp][0].z, v[pp][0].w, v[pp][1].x, v[pp][1].y, v[pp][1].z, v[pp][1].w};
             const float qq[8] = {q[pp][0].x, q[pp][0].y, q[pp][0].z, q[pp][0].w, q[pp][1].x, q[pp][1].y, q[pp][1].z, q[pp][1].w};
             float e[8];
@@ -393,8 +408,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
   } else {
     // ============= epilogue (warps 0-7: thread = (TMEM lane = row, column half)) ==========================
     const int r = (warp & 3) * 32 + lane;
-    const int hf = warp >> 2;
-    constexpr int HC = H / 2;
+    const int hf = warp >> 2;               // column half owned by this warp (always 0 when NHALF == 1)
+    constexpr int HC = H / NHALF;           // columns per thread
     constexpr int NCH = HC / 32;
     const uint32_t s_i = sbase + S::OFF_SI;          // int   [128] receiver per row
     const uint32_t s_dx = sbase + S::OFF_DX;         // float [128][4]
@@ -484,10 +499,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
         }
         TC_PROF(const long long te3 = clock64(); te_p1 += te3 - te2;)
-        sts32f(s_dot + (hf * TM + r) * 4, dot);
-        if (MODE == MODE_GCL) tmem_st_wait();
-        named_bar_sync(2 + (warp & 3), 64);
-        const float full_dot = lds32f(s_dot + r * 4) + lds32f(s_dot + (TM + r) * 4);
+        float full_dot = dot;
+        if (NHALF == 2) {                       // the two warps sharing this lane quarter exchange their partial dots
+          sts32f(s_dot + (hf * TM + r) * 4, dot);
+          if (MODE == MODE_GCL) tmem_st_wait();
+          named_bar_sync(2 + (warp & 3), 64);
+          full_dot = lds32f(s_dot + r * 4) + lds32f(s_dot + (TM + r) * 4);
+        } else {
+          __syncwarp();                         // s_i of this warp's rows is visible to its lanes
+        }
         const int prev_i = __shfl_up_sync(0xffffffffu, my_i, 1);
         const bool head = valid && (lane == 0 || prev_i != my_i);
         const unsigned hm = __ballot_sync(0xffffffffu, head);
@@ -516,7 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc16_kernel(const Args a) {
             }
             __syncwarp();
           }
-          named_bar_sync(2 + (warp & 3), 64);
+          if (NHALF == 2) named_bar_sync(2 + (warp & 3), 64);
         } else {
           float g = a.attention ? sigmoidf_(full_dot + __ldg(a.b_out)) : 1.0f;
           if (!valid) g = 0.f;
@@ -601,7 +621,7 @@ int launch_mode(const Args& a, cudaStream_t st) {
   args.rz_scale = 1.0f + RZ_BIAS_PER_MMA * (float)(a.n_slabs * (BK / 16) * 3);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NTHREADS);
+  cfg.blockDim = dim3(Roles<MODE>::NTHREADS);
   cfg.dynamicSmemBytes = S::ALLOC;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
