@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgeoldm_b200.so")
+LIB_PATH = os.environ.get("GEOLDM_B200_LIB") or os.path.join(HERE, "csrc", "libgeoldm_b200.so")   # env: A/B builds
 
 MAX_LAYERS, MAX_SUBLAYERS = 16, 4
 MMA_FP32_SIMT, MMA_3XTF32, MMA_TF32, MMA_BF16, MMA_3XF16 = 0, 1, 2, 3, 4

@@ -76,7 +76,9 @@ struct Args {
 template <int H, int MODE>
 struct Smem {
   static constexpr int NAS = (MODE == 0) ? 2 : 3;
-  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 36 * 4 : 0u;
+  // warp-private [32 rows][36 floats] transposition tiles: GCL 8 warps (segment sum), DENSE / RAW 4 warps (coalesced
+  // output rows); EQUIV needs none
+  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 36 * 4 : (MODE == 1) ? 0u : 4u * 32 * 36 * 4;
   static constexpr uint32_t NH = H / 2;
   static constexpr uint32_t W_IMG = NH * 128u;
   static constexpr uint32_t W_STAGE = 2u * W_IMG;
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
   uint64_t* w_peer = bars + 2 * NWS + 2 * NAS + 4;    // [NWS] the peer CTA's N-half of the W stage has landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
 
+  TC_PROF(const long long t_entry = clock64();)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
@@ -449,31 +452,76 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       const uint32_t taddr = tlane + region * 256;
 
       if (MODE == MODE_DENSE || MODE == MODE_RAW) {
-        float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
-        const float* rrow = (MODE == MODE_DENSE && a.epi == 2) ? a.res + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC : nullptr;
-        const float* bias = (MODE == MODE_DENSE && a.b2) ? a.b2 + nb * H + hf * HC : nullptr;
+        if (MODE == MODE_DENSE && a.epi == 2) {
+          // residual epilogue: row-per-lane (each thread re-reads and writes its own row; measured faster than the
+          // transposed form for this read-modify-write pattern)
+          float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
+          const float* rrow = (MODE == MODE_DENSE && a.epi == 2) ? a.res + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC : nullptr;
+          const float* bias = (MODE == MODE_DENSE && a.b2) ? a.b2 + nb * H + hf * HC : nullptr;
 #pragma unroll 1
-        for (int cc = 0; cc < NCH; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(taddr + cc * 32, v);
-          tmem_ld_wait();
-          if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }     // registers hold the last chunk
-          if (valid) {
+          for (int cc = 0; cc < NCH; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            tmem_ld_wait();
+            if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }     // registers hold the last chunk
+            if (valid) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              float o[4] = {__uint_as_float(v[c4 * 4]) * scale, __uint_as_float(v[c4 * 4 + 1]) * scale,
-                            __uint_as_float(v[c4 * 4 + 2]) * scale, __uint_as_float(v[c4 * 4 + 3]) * scale};
-              if (bias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + c4 * 4));
-                o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+              for (int c4 = 0; c4 < 8; ++c4) {
+                float o[4] = {__uint_as_float(v[c4 * 4]) * scale, __uint_as_float(v[c4 * 4 + 1]) * scale,
+                              __uint_as_float(v[c4 * 4 + 2]) * scale, __uint_as_float(v[c4 * 4 + 3]) * scale};
+                if (bias) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + c4 * 4));
+                  o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+                }
+                if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
+                if (rrow) {
+                  const float4 rs = __ldg(reinterpret_cast<const float4*>(rrow + cc * 32 + c4 * 4));
+                  o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
+                }
+                *reinterpret_cast<float4*>(orow + cc * 32 + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
               }
-              if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
-              if (rrow) {
-                const float4 rs = __ldg(reinterpret_cast<const float4*>(rrow + cc * 32 + c4 * 4));
-                o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
-              }
-              *reinterpret_cast<float4*>(orow + cc * 32 + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
             }
+          }
+        } else {
+          // lane = accumulator row after tcgen05.ld; a row-per-lane global store would touch 32 lines per instruction, so
+          // every 32 x 32 chunk goes through this warp's transposition tile and leaves as 4 rows x 128 contiguous bytes per
+          // instruction (lane = (row % 4, 16-byte column group)), with bias / SiLU / residual applied on the way out
+          const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);
+          const int wrow0 = row0 + (warp & 3) * 32;                 // first global row of this warp's 32 rows
+          const int nval = min(32, nrows - (warp & 3) * 32);        // rows of this warp that exist (may be <= 0)
+          const int orow_l = lane >> 3, ocol = (lane & 7) * 4;
+          const size_t col0 = (size_t)nb * H + hf * HC;
+          const bool has_res = (MODE == MODE_DENSE && a.epi == 2);
+          const float* bias = (MODE == MODE_DENSE && a.b2) ? a.b2 + col0 : nullptr;
+#pragma unroll 1
+          for (int cc = 0; cc < NCH; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            tmem_ld_wait();
+            if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }     // registers hold the last chunk
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              sts128f(Tw + (lane * 36 + c4 * 4) * 4, make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
+                                                                 __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3])));
+            __syncwarp();
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + ocol));
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+              const int rl = it8 * 4 + orow_l;
+              if (rl < nval) {
+                const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
+                float o[4] = {fmaf(t.x, scale, b4.x), fmaf(t.y, scale, b4.y), fmaf(t.z, scale, b4.z), fmaf(t.w, scale, b4.w)};
+                if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
+                const size_t goff = (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol;
+                if (has_res) {
+                  const float4 rs = __ldg(reinterpret_cast<const float4*>(a.res + goff));
+                  o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
+                }
+                *reinterpret_cast<float4*>(a.out + goff) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            }
+            __syncwarp();
           }
         }
       } else {
@@ -595,6 +643,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
+  TC_PROF(if (tid == 0 && blockIdx.x == 0) g_tc16_stats[15] += (unsigned long long)(clock64() - t_entry);)
 }
 
 template <int H, int MODE>

@@ -30,14 +30,19 @@ for name, fn, em, o in (("GCL", L.geoldm_edge_gcl, w.block[0].gcl[0].edge, torch
     for _ in range(3):
         _lib.check(fn(C.byref(ccfg), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xx), _lib.ptr(xx), _lib.ptr(o), None), name)
     L.geoldm_tc16_read_stats(out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(5):
         _lib.check(fn(C.byref(ccfg), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xx), _lib.ptr(xx), _lib.ptr(o), None), name)
+    e1.record()
     L.geoldm_tc16_read_stats(out)
+    print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us per launch (events, 5 back-to-back launches)")
     v = [float(out[i]) for i in range(16)]
     t = v[5]
     print(f"{name}: per tile-pair cycles: MMA thread total {v[0]/t:.0f} | wait acc_empty {v[1]/t:.0f} | wait a_full {v[2]/t:.0f} | "
           f"wait w {v[3]/t:.0f} | issue+other {(v[0]-v[1]-v[2]-v[3])/t:.0f}   ({v[4]:.0f} launches, {t/v[4]:.0f} tile-pairs per CTA)")
     print(f"   producer thread: wait a_empty(+loads) {v[6]/t:.0f} | compute+store {v[7]/t:.0f} | fence+arrive {v[8]/t:.0f} | metadata {v[9]/t:.0f}")
+    print(f"   CTA 0 entry->exit {v[15]/v[4]:.0f} cycles per launch = {v[15]/v[4]/1.965e3:.1f} us")
     print(f"   epilogue thread: wait acc_full {v[10]/t:.0f} | pass 1 {v[11]/t:.0f} | dot exchange+gate {v[12]/t:.0f} | pass 2 {v[13]/t:.0f} | metadata {v[14]/t:.0f}")
 
 # ---- node-level (dense) launches of one block ---------------------------------------------------------------------
@@ -65,5 +70,6 @@ for name, fn in cases:
     t = v[5]
     print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us/launch; CTA 0: {t/v[4]:.0f} tile-pairs, MMA thread total/launch {v[0]/v[4]:.0f} cycles; per tile-pair: "
           f"wait acc_empty {v[1]/t:.0f} | wait a_full {v[2]/t:.0f} | wait w {v[3]/t:.0f} | issue {(v[0]-v[1]-v[2]-v[3])/t:.0f}")
+    print(f"   CTA 0 entry->exit {v[15]/v[4]:.0f} cycles per launch = {v[15]/v[4]/1.965e3:.1f} us")
     print(f"   producer: wait a_empty(+loads) {v[6]/t:.0f} | compute+store {v[7]/t:.0f} | fence+arrive {v[8]/t:.0f} | metadata {v[9]/t:.0f};"
           f"  epilogue: wait acc_full {v[10]/t:.0f} | metadata {v[14]/t:.0f}")
