@@ -41,7 +41,7 @@ constexpr int NWS = 3;           // W pipeline stages
 // tail (second SiLU, gate, segment sum) is as long as its A generation.
 template <int MODE>
 struct Roles {
-  static constexpr int EPI_W = (MODE == 0) ? 8 : 4;
+  static constexpr int EPI_W = (MODE == 0 || MODE == 1) ? 8 : 4;
   static constexpr int PROD_W = (MODE == 0) ? 8 : 16;
   static constexpr int WARP_LOAD = EPI_W + PROD_W, WARP_MMA = WARP_LOAD + 1;
   static constexpr int NTHREADS = 32 * (EPI_W + PROD_W + 2);
