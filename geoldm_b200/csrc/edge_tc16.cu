@@ -10,7 +10,8 @@
 // so the fused tail of tile t overlaps the MMAs of tile t+1 and the A generation of tile t+2.
 // The weight images carry a power-of-two scale 2^e (chosen by geoldm_tc_pack16 so that max|w| 2^e is in [2^13, 2^14)):
 // it keeps w_lo out of the fp16 subnormal range; the epilogue folds 2^-e into the round-toward-zero compensation
-// factor.  Activations are not scaled (|a| < 65504 required; a_lo below 2^-14 is subnormal: absolute error <= 2^-25).
+// factor.  Activations are not scaled: |a| < 65504 is required for full accuracy (larger values saturate, they do not become
+// inf / NaN); a_lo below 2^-14 is subnormal: absolute error <= 2^-25.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -113,16 +114,21 @@ __device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t adesc, ui
       : "memory");
 }
 
+// two fp32 -> packed fp16x2 (first argument in the low half), round to nearest, overflow saturates to +-65504 instead of
+// becoming inf: an out-of-range activation then degrades the product instead of poisoning the tile with NaN
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_half, float hi_half) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+  return r;
+}
 // 8 fp32 -> 8 fp16 hi + 8 fp16 lo (lo = fp16(v - hi), exact subtraction), packed for one 16-byte swizzle chunk
 __device__ __forceinline__ void split_f16x8(const float (&e)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half2 hh = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
-    const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(e[2 * i] - hf.x, e[2 * i + 1] - hf.y);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    h[i] = pack_f16x2_sat(e[2 * i], e[2 * i + 1]);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+    l[i] = pack_f16x2_sat(e[2 * i] - hf.x, e[2 * i + 1] - hf.y);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -468,3 +468,28 @@ def test_fix_noise_and_context_paths(dev):
     _, _, x2, _ = sample(args, dev, model, {"max_n_nodes": 29}, nodesxsample=nodes, context=ctx, fix_noise=False, seed=11)
     assert O.err_metric(x2[0].cpu(), x2[1].cpu()) > 1e-2
     assert bool(torch.isfinite(x2).all())
+
+
+def test_f16_split_saturates_instead_of_nan(dev):
+    """3xf16: activations beyond the fp16 range (|a| >= 65504) saturate; the result degrades but stays finite."""
+    if not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    from geoldm_b200 import _lib
+    L = _lib.lib()
+    H, m = 128, 200
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(m, H, generator=g)
+    a[5, 7] = 3.0e5
+    a[9, 1] = -7.0e6
+    w = torch.randn(H, H, generator=g) / np.sqrt(H)
+    A, W = a.to(dev), w.to(dev)
+    pack = _tc_pack(L, _lib, 16, H, W, H, H, dev)
+    out = torch.empty(m, H, device=dev)
+    _lib.check(L.geoldm_linear_tc(H, 16, _lib.ptr(A), H, None, 0, 1.0, _lib.ptr(pack), 1, None, None, 0, _lib.ptr(out), m,
+                                  None), "linear_tc")
+    out = out.cpu()
+    assert torch.isfinite(out).all()
+    ref = a.double() @ w.double().T
+    ok = torch.ones(m, dtype=torch.bool)
+    ok[5] = ok[9] = False
+    assert O.err_metric(out[ok].double(), ref[ok]) < 5e-6          # rows without out-of-range entries are unaffected
