@@ -42,7 +42,7 @@ constexpr int NWS = 3;           // W pipeline stages
 // tail (second SiLU, gate, segment sum) is as long as its A generation.
 template <int MODE>
 struct Roles {
-  static constexpr int EPI_W = (MODE == 0 || MODE == 1) ? 8 : 4;
+  static constexpr int EPI_W = 8;
   static constexpr int PROD_W = (MODE == 0) ? 8 : 16;
   static constexpr int WARP_LOAD = EPI_W + PROD_W, WARP_MMA = WARP_LOAD + 1;
   static constexpr int NTHREADS = 32 * (EPI_W + PROD_W + 2);
@@ -76,10 +76,10 @@ struct Args {
 
 template <int H, int MODE>
 struct Smem {
-  static constexpr int NAS = (MODE == 0) ? 2 : 3;
+  static constexpr int NAS = (MODE == 1) ? 3 : 2;             // A pipeline stages (the others spend 36 KB on transposition tiles)
   // warp-private [32 rows][36 floats] transposition tiles: GCL 8 warps (segment sum), DENSE / RAW 4 warps (coalesced
   // output rows); EQUIV needs none
-  static constexpr uint32_t T_BYTES = (MODE == 0) ? 8u * 32 * 36 * 4 : (MODE == 1) ? 0u : 4u * 32 * 36 * 4;
+  static constexpr uint32_t T_BYTES = (MODE == 1) ? 0u : 8u * 32 * 36 * 4;
   static constexpr uint32_t NH = H / 2;
   static constexpr uint32_t W_IMG = NH * 128u;
   static constexpr uint32_t W_STAGE = 2u * W_IMG;
