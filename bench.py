@@ -182,8 +182,8 @@ def workload_config(n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)      # ~1 s timed: long enough to sit at the sustained (power-capped) clocks
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mma-mode", default=os.environ.get("GEOLDM_MMA_MODE", "auto"))
     ap.add_argument("--no-e2e", action="store_true")

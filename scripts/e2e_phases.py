@@ -17,7 +17,7 @@ def main():
     torch.cuda.set_device(dev)
     n_mol = int(os.environ.get("MOLS", 1250))
     from geoldm_b200.models import get_latent_diffusion
-    margs = bench.qm9_args("3xtf32")
+    margs = bench.qm9_args(os.environ.get("MODE", "3xf16"))
     info = {"atom_decoder": ["H", "C", "N", "O", "F"], "n_nodes": {5: 1}, "max_n_nodes": 29}
     torch.manual_seed(0)
     model, _, _ = get_latent_diffusion(margs, dev, info, None)
