@@ -73,6 +73,223 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
 }  // namespace
 }  // namespace geoldm
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused element-wise stages of the edge MLPs for the autograd path (train.py): one warp per edge, lanes stride over the
+// H columns (coalesced 128-byte rows), everything recomputed from the GEMM inputs/outputs in the backward pass so that
+// no [E, H] intermediate besides the GEMM operands is kept.  Accurate expf (training is not the hot loop).
+//   act   : a[e][k] = SiLU(P[i_e][k] + Q[j_e][k] + r_e w_r[k] + d0_e w_d[k])                  (egnn_new.py:30-36, split form)
+//   tail  : m = SiLU(mpre + b2);  gate: agg[i_e] += m sigmoid(m.w_att + b_att) / div        (:37-44, :258-267)
+//           head: sc[e] = m.w                                                                 (:86-90)
+// ---------------------------------------------------------------------------------------------------------------
+namespace geoldm {
+namespace {
+constexpr int MAXC = 8;   // columns per lane: H <= 256
+
+__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void edge_act_fwd_kernel(int E, int H, const float* __restrict__ pq, int pq_ld, const float* __restrict__ r,
+                                    const float* __restrict__ d0, const float* __restrict__ w_rd,
+                                    const int* __restrict__ ei, const int* __restrict__ ej, float* __restrict__ a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int e = warp; e < E; e += nwarp) {
+    const float* P = pq + (size_t)ei[e] * pq_ld;
+    const float* Q = pq + (size_t)ej[e] * pq_ld + H;
+    const float re = r[e], de = d0[e];
+    for (int c = lane; c < H; c += 32) {
+      const float z = P[c] + Q[c] + re * w_rd[c] + de * w_rd[H + c];
+      a[(size_t)e * H + c] = z * sigm(z);
+    }
+  }
+}
+
+__global__ void edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, int pq_ld, const float* __restrict__ r,
+                                    const float* __restrict__ d0, const float* __restrict__ w_rd,
+                                    const int* __restrict__ ei, const int* __restrict__ ej, const float* __restrict__ da,
+                                    float* __restrict__ dpq, float* __restrict__ dr, float* __restrict__ dd0,
+                                    float* __restrict__ dw_rd) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  float acc_r[MAXC], acc_d[MAXC];
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) acc_r[k] = acc_d[k] = 0.f;
+  for (int e = warp; e < E; e += nwarp) {
+    const int i = ei[e], j = ej[e];
+    const float* P = pq + (size_t)i * pq_ld;
+    const float* Q = pq + (size_t)j * pq_ld + H;
+    const float re = r[e], de = d0[e];
+    float sr = 0.f, sd = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H) {
+        const float wr = w_rd[c], wd = w_rd[H + c];
+        const float z = P[c] + Q[c] + re * wr + de * wd;
+        const float s = sigm(z);
+        const float g = da[(size_t)e * H + c] * (s * (1.0f + z * (1.0f - s)));     // d SiLU / dz
+        atomicAdd(dpq + (size_t)i * pq_ld + c, g);
+        atomicAdd(dpq + (size_t)j * pq_ld + H + c, g);
+        sr += g * wr; sd += g * wd;
+        acc_r[k] += g * re; acc_d[k] += g * de;
+      }
+    }
+    sr = warp_sum_f(sr); sd = warp_sum_f(sd);
+    if (lane == 0) { dr[e] = sr; dd0[e] = sd; }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    const int c = lane + 32 * k;
+    if (c < H) { atomicAdd(dw_rd + c, acc_r[k]); atomicAdd(dw_rd + H + c, acc_d[k]); }
+  }
+}
+
+// gate != 0: agg[i] += m * sigmoid(m.w + b) / div (attention != 0) or m / div; gate == 0: sc[e] = m.w
+__global__ void edge_tail_fwd_kernel(int E, int H, const float* __restrict__ mpre, const float* __restrict__ b2,
+                                     const float* __restrict__ w, const float* __restrict__ bw, int gate, int attention,
+                                     const int* __restrict__ ei, float inv_div, float* __restrict__ agg,
+                                     float* __restrict__ sc) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int e = warp; e < E; e += nwarp) {
+    float m[MAXC];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      m[k] = 0.f;
+      if (c < H) {
+        const float z = mpre[(size_t)e * H + c] + b2[c];
+        m[k] = z * sigm(z);
+        if (w) dot += m[k] * w[c];
+      }
+    }
+    dot = warp_sum_f(dot);
+    if (!gate) { if (lane == 0) sc[e] = dot; continue; }
+    const float g = attention ? sigm(dot + bw[0]) : 1.0f;
+    float* out = agg + (size_t)ei[e] * H;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H) atomicAdd(out + c, m[k] * g * inv_div);
+    }
+  }
+}
+
+__global__ void edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpre, const float* __restrict__ b2,
+                                     const float* __restrict__ w, const float* __restrict__ bw, int gate, int attention,
+                                     const int* __restrict__ ei, float inv_div, const float* __restrict__ dagg,
+                                     const float* __restrict__ dsc, float* __restrict__ dmpre, float* __restrict__ db2,
+                                     float* __restrict__ dw, float* __restrict__ dbw) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  float acc_b[MAXC], acc_w[MAXC];
+  float acc_bw = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) acc_b[k] = acc_w[k] = 0.f;
+  for (int e = warp; e < E; e += nwarp) {
+    float m[MAXC], dz[MAXC], de[MAXC];
+    float dot = 0.f, dg = 0.f;
+    const float* din = gate ? dagg + (size_t)ei[e] * H : nullptr;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      m[k] = dz[k] = de[k] = 0.f;
+      if (c < H) {
+        const float z = mpre[(size_t)e * H + c] + b2[c];
+        const float s = sigm(z);
+        m[k] = z * s;
+        dz[k] = s * (1.0f + z * (1.0f - s));
+        if (w) dot += m[k] * w[c];
+        if (gate) { de[k] = din[c] * inv_div; dg += de[k] * m[k]; }
+      }
+    }
+    dot = warp_sum_f(dot);
+    float g = 1.0f, ds;
+    if (gate) {
+      dg = warp_sum_f(dg);
+      ds = 0.f;
+      if (attention) { g = sigm(dot + bw[0]); ds = dg * g * (1.0f - g); }
+    } else {
+      ds = dsc[e];
+    }
+    if (lane == 0 && dbw) acc_bw += ds;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H) {
+        float dm = gate ? de[k] * g : 0.f;
+        if (w) { dm += ds * w[c]; acc_w[k] += ds * m[k]; }
+        const float o = dm * dz[k];
+        dmpre[(size_t)e * H + c] = o;
+        acc_b[k] += o;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    const int c = lane + 32 * k;
+    if (c < H) { atomicAdd(db2 + c, acc_b[k]); if (dw) atomicAdd(dw + c, acc_w[k]); }
+  }
+  if (lane == 0 && dbw) atomicAdd(dbw, acc_bw);
+}
+
+inline int train_grid(int E) { int b = (E + 7) / 8; return b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b); }
+}  // namespace
+}  // namespace geoldm
+
+extern "C" {
+int geoldm_train_edge_act_fwd(int n_edge, int H, const float* pq, int pq_ld, const float* r, const float* d0,
+                              const float* w_rd, const int* edge_i, const int* edge_j, float* a, void* stream) {
+  using namespace geoldm;
+  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_act: H=%d not in (0, %d]", H, 32 * MAXC);
+  if (n_edge == 0) return 0;
+  edge_act_fwd_kernel<<<train_grid(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, pq, pq_ld, r, d0, w_rd, edge_i, edge_j, a);
+  GEOLDM_CHECK_LAUNCH("edge_act_fwd_kernel");
+  return 0;
+}
+int geoldm_train_edge_act_bwd(int n_edge, int H, const float* pq, int pq_ld, const float* r, const float* d0,
+                              const float* w_rd, const int* edge_i, const int* edge_j, const float* da, float* dpq,
+                              float* dr, float* dd0, float* dw_rd, void* stream) {
+  using namespace geoldm;
+  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_act: H=%d not in (0, %d]", H, 32 * MAXC);
+  if (n_edge == 0) return 0;
+  edge_act_bwd_kernel<<<train_grid(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, pq, pq_ld, r, d0, w_rd, edge_i, edge_j, da,
+                                                                           dpq, dr, dd0, dw_rd);
+  GEOLDM_CHECK_LAUNCH("edge_act_bwd_kernel");
+  return 0;
+}
+int geoldm_train_edge_tail_fwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
+                               int gate, int attention, const int* edge_i, float div, float* agg, float* sc,
+                               void* stream) {
+  using namespace geoldm;
+  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_tail: H=%d not in (0, %d]", H, 32 * MAXC);
+  GEOLDM_REQUIRE(gate ? (agg != nullptr && (!attention || (w && bw))) : (sc != nullptr && w != nullptr), "train_edge_tail: bad arguments%s", "");
+  if (n_edge == 0) return 0;
+  edge_tail_fwd_kernel<<<train_grid(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, attention || !gate ? w : nullptr, bw, gate,
+                                                                            attention, edge_i, 1.0f / div, agg, sc);
+  GEOLDM_CHECK_LAUNCH("edge_tail_fwd_kernel");
+  return 0;
+}
+int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
+                               int gate, int attention, const int* edge_i, float div, const float* dagg, const float* dsc,
+                               float* dmpre, float* db2, float* dw, float* dbw, void* stream) {
+  using namespace geoldm;
+  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_tail: H=%d not in (0, %d]", H, 32 * MAXC);
+  if (n_edge == 0) return 0;
+  const bool use_w = attention || !gate;
+  edge_tail_bwd_kernel<<<train_grid(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, use_w ? w : nullptr, bw, gate, attention,
+                                                                            edge_i, 1.0f / div, dagg, dsc, dmpre, db2,
+                                                                            use_w ? dw : nullptr, (gate && attention) ? dbw : nullptr);
+  GEOLDM_CHECK_LAUNCH("edge_tail_bwd_kernel");
+  return 0;
+}
+}
+
 extern "C" int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
                               void* stream) {
   using namespace geoldm;

@@ -3,8 +3,10 @@
 Correctness-first companion of the fused inference kernels: the network is evaluated on the same ragged packing, every
 ``nn.Linear`` with GEMM-sized dimensions runs on this repo's fp32 CUDA kernels in all three directions
 (forward ``geoldm_linear``, input gradient ``geoldm_linear`` with the untransposed weight, weight gradient
-``geoldm_gemm_tn``) through ``torch.autograd.Function``; gathers, segment sums (``index_add_``) and element-wise maths are
-library ops recorded by autograd.  It shares the ``nn.Parameter`` objects of the inference modules, so optimisers, EMA and
+``geoldm_gemm_tn``) through ``torch.autograd.Function``, and the element-wise stages of both edge MLPs (gather + first
+SiLU; bias + second SiLU + attention gate + segment sum / coordinate head) run as fused forward/backward CUDA kernels
+(``geoldm_train_edge_act_*``, ``geoldm_train_edge_tail_*``, csrc/train.cu).  The remaining node-level element-wise ops, the
+1-3-wide heads and ``coord2diff`` are library ops recorded by autograd.  It shares the ``nn.Parameter`` objects of the inference modules, so optimisers, EMA and
 ``DistributedDataParallel`` (NCCL gradient all-reduce) work unchanged.  A fused recompute-in-kernel backward on the
 tensor cores is round-2 work.
 
@@ -72,26 +74,103 @@ def linear(x, weight, bias=None):
     return F.linear(x, weight, bias)
 
 
+class _EdgeActFn(torch.autograd.Function):
+    """a[e] = SiLU(P[i_e] + Q[j_e] + r_e w_r + d0_e w_d) on `geoldm_train_edge_act_*` (forward and backward fused,
+    the pre-activation is recomputed in the backward pass)."""
+
+    @staticmethod
+    def forward(ctx, pq, r, d0, w_rd, ei32, ej32):
+        pq, r, d0, w_rd = pq.contiguous(), r.contiguous(), d0.contiguous(), w_rd.contiguous()
+        E, H = ei32.numel(), w_rd.shape[1]
+        a = torch.empty(E, H, device=pq.device, dtype=torch.float32)
+        _lib.check(_lib.lib().geoldm_train_edge_act_fwd(E, H, _lib.ptr(pq), pq.shape[1], _lib.ptr(r), _lib.ptr(d0),
+                                                        _lib.ptr(w_rd), _lib.ptr(ei32), _lib.ptr(ej32), _lib.ptr(a),
+                                                        _stream(pq)), "train_edge_act_fwd")
+        ctx.save_for_backward(pq, r, d0, w_rd, ei32, ej32)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        pq, r, d0, w_rd, ei32, ej32 = ctx.saved_tensors
+        E, H = ei32.numel(), w_rd.shape[1]
+        da = da.contiguous()
+        dpq = torch.zeros_like(pq)
+        dw = torch.zeros_like(w_rd)
+        dr = torch.empty(E, device=pq.device, dtype=torch.float32)
+        dd0 = torch.empty(E, device=pq.device, dtype=torch.float32)
+        _lib.check(_lib.lib().geoldm_train_edge_act_bwd(E, H, _lib.ptr(pq), pq.shape[1], _lib.ptr(r), _lib.ptr(d0),
+                                                        _lib.ptr(w_rd), _lib.ptr(ei32), _lib.ptr(ej32), _lib.ptr(da),
+                                                        _lib.ptr(dpq), _lib.ptr(dr), _lib.ptr(dd0), _lib.ptr(dw),
+                                                        _stream(pq)), "train_edge_act_bwd")
+        return dpq, dr.view_as(r), dd0.view_as(d0), dw, None, None
+
+
+class _EdgeTailFn(torch.autograd.Function):
+    """m = SiLU(mpre + b2) followed by the gated segment sum (gate=True -> agg [N, H]) or the head dot product
+    (gate=False -> sc [E, 1]) on `geoldm_train_edge_tail_*`."""
+
+    @staticmethod
+    def forward(ctx, mpre, b2, w, bw, ei32, n_node, div, gate, attention):
+        mpre, b2 = mpre.contiguous(), b2.contiguous()
+        E, H = mpre.shape
+        w = None if w is None else w.contiguous()
+        dev = mpre.device
+        agg = torch.zeros(n_node, H, device=dev, dtype=torch.float32) if gate else None
+        sc = None if gate else torch.empty(E, 1, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().geoldm_train_edge_tail_fwd(E, H, _lib.ptr(mpre), _lib.ptr(b2), _lib.ptr(w), _lib.ptr(bw),
+                                                         int(gate), int(attention), _lib.ptr(ei32), float(div),
+                                                         _lib.ptr(agg), _lib.ptr(sc), _stream(mpre)), "train_edge_tail_fwd")
+        ctx.save_for_backward(mpre, b2, w, bw, ei32)
+        ctx.cfg = (float(div), bool(gate), bool(attention))
+        return agg if gate else sc
+
+    @staticmethod
+    def backward(ctx, dout):
+        mpre, b2, w, bw, ei32 = ctx.saved_tensors
+        div, gate, attention = ctx.cfg
+        E, H = mpre.shape
+        dout = dout.contiguous()
+        dmpre = torch.empty_like(mpre)
+        db2 = torch.zeros_like(b2)
+        dw = None if w is None else torch.zeros_like(w)
+        dbw = None if bw is None else torch.zeros_like(bw)
+        _lib.check(_lib.lib().geoldm_train_edge_tail_bwd(E, H, _lib.ptr(mpre), _lib.ptr(b2), _lib.ptr(w), _lib.ptr(bw),
+                                                         int(gate), int(attention), _lib.ptr(ei32), div,
+                                                         _lib.ptr(dout) if gate else None, None if gate else _lib.ptr(dout),
+                                                         _lib.ptr(dmpre), _lib.ptr(db2), _lib.ptr(dw), _lib.ptr(dbw),
+                                                         _stream(mpre)), "train_edge_tail_bwd")
+        if w is not None and not (attention or not gate):
+            dw = None
+        return dmpre, db2, dw, dbw, None, None, None, None, None
+
+
+def _fused_ok(h, H):
+    return h.is_cuda and h.dtype == torch.float32 and H <= 256 and H % 16 == 0
+
+
 def _coord2diff(x, ei, ej, norm_constant):
     d = x.index_select(0, ei) - x.index_select(0, ej)
     r = (d * d).sum(1, keepdim=True)
     return r, d / (torch.sqrt(r + 1e-8) + norm_constant)
 
 
-def _edge_mlp(h, first, second, ei, ej, r, d0, H):
-    """Split first layer (per-node projections + two distance columns) and second layer, both + SiLU."""
+def _edge_pre(h, first, ei, ej, r, d0, H, e32):
+    """First edge layer in split form: per-node projections + the two distance columns, then SiLU."""
     w1 = first.weight
     wpq = torch.cat([w1[:, :H], w1[:, H:2 * H]], dim=0)                     # [2H, H]
     bpq = torch.cat([first.bias, torch.zeros_like(first.bias)])
     pq = linear(h, wpq, bpq)
+    if _fused_ok(h, H):
+        return _EdgeActFn.apply(pq, r.reshape(-1), d0.reshape(-1), w1[:, 2 * H:2 * H + 2].t(), e32[0], e32[1])
     pre1 = pq[:, :H].index_select(0, ei) + pq[:, H:].index_select(0, ej) + r * w1[:, 2 * H] + d0 * w1[:, 2 * H + 1]
-    return F.silu(linear(F.silu(pre1), second.weight, second.bias))
+    return F.silu(pre1)
 
 
 def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
     """EGNN.forward with autograd on ragged tensors: h [N, in_nf], x [N, 3] -> (h [N, out_nf], x [N, 3])."""
     H = egnn.hidden_nf
     ei, ej = batch.edge_i.long(), batch.edge_j.long()
+    e32 = (batch.edge_i.to(torch.int32).contiguous(), batch.edge_j.to(torch.int32).contiguous())
     N = batch.n_node
     if egnn.aggregation_method == "mean":
         if batch.n_max <= 0:
@@ -99,6 +178,7 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
         div = float(batch.n_max)
     else:
         div = float(egnn.normalization_factor)
+    fused = _fused_ok(h, H)
     d0, _ = _coord2diff(x, ei, ej, 1.0)
     h = F.linear(h, egnn.embedding.weight, egnn.embedding.bias)
     for b in range(egnn.n_layers):
@@ -106,15 +186,27 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
         r, u = _coord2diff(x, ei, ej, float(egnn.norm_constant))
         for s in range(egnn.inv_sublayers):
             g = getattr(blk, f"gcl_{s}")
-            m = _edge_mlp(h, g.edge_mlp[0], g.edge_mlp[2], ei, ej, r, d0, H)
-            if egnn.attention:
-                m = m * torch.sigmoid(F.linear(m, g.att_mlp[0].weight, g.att_mlp[0].bias))
-            agg = torch.zeros(N, H, device=h.device, dtype=h.dtype).index_add_(0, ei, m) / div
+            a1 = _edge_pre(h, g.edge_mlp[0], ei, ej, r, d0, H, e32)
+            if fused:      # second layer without bias; bias + SiLU + gate + segment sum in one kernel
+                att_w = g.att_mlp[0].weight.reshape(H) if egnn.attention else None
+                att_b = g.att_mlp[0].bias if egnn.attention else None
+                agg = _EdgeTailFn.apply(linear(a1, g.edge_mlp[2].weight, None), g.edge_mlp[2].bias, att_w, att_b, e32[0],
+                                        N, div, True, bool(egnn.attention))
+            else:
+                m = F.silu(linear(a1, g.edge_mlp[2].weight, g.edge_mlp[2].bias))
+                if egnn.attention:
+                    m = m * torch.sigmoid(F.linear(m, g.att_mlp[0].weight, g.att_mlp[0].bias))
+                agg = torch.zeros(N, H, device=h.device, dtype=h.dtype).index_add_(0, ei, m) / div
             t1 = F.silu(linear(torch.cat([h, agg], dim=1), g.node_mlp[0].weight, g.node_mlp[0].bias))
             h = h + linear(t1, g.node_mlp[2].weight, g.node_mlp[2].bias)
         q = blk.gcl_equiv
-        m2 = _edge_mlp(h, q.coord_mlp[0], q.coord_mlp[2], ei, ej, r, d0, H)
-        sc = F.linear(m2, q.coord_mlp[4].weight)
+        a2 = _edge_pre(h, q.coord_mlp[0], ei, ej, r, d0, H, e32)
+        if fused:
+            sc = _EdgeTailFn.apply(linear(a2, q.coord_mlp[2].weight, None), q.coord_mlp[2].bias,
+                                   q.coord_mlp[4].weight.reshape(H), None, e32[0], N, div, False, False)
+        else:
+            m2 = F.silu(linear(a2, q.coord_mlp[2].weight, q.coord_mlp[2].bias))
+            sc = F.linear(m2, q.coord_mlp[4].weight)
         trans = u * torch.tanh(sc) * egnn.coords_range if egnn.tanh else u * sc
         x = x + torch.zeros(N, 3, device=x.device, dtype=x.dtype).index_add_(0, ei, trans) / div
     h = F.linear(h, egnn.embedding_out.weight, egnn.embedding_out.bias)

@@ -190,6 +190,24 @@ int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, con
  * zeroes C; lda/ldb multiples of 4).  Forward and input-gradient GEMMs of a Linear layer use geoldm_linear. */
 int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
                    void* stream);
+/* Fused element-wise stages of the edge MLPs for the autograd path (forward + backward, everything recomputed from the
+ * GEMM operands; one warp per edge; H <= 256).  pq [N][pq_ld] = P | Q projections; r, d0 [E] squared distances;
+ * w_rd [2][H]; outputs of the backward kernels that are sums over edges (dpq, dw_rd, db2, dw, dbw) are ACCUMULATED with
+ * atomics into caller-zeroed buffers.
+ *   act : a[e] = SiLU(P[i_e] + Q[j_e] + r_e w_r + d0_e w_d)
+ *   tail: m = SiLU(mpre + b2); gate != 0: agg[i_e] += m * (attention ? sigmoid(m.w + bw) : 1) / div;
+ *                              gate == 0: sc[e] = m.w                       (egnn_new.py:30-45, 86-90, 258-267) */
+int geoldm_train_edge_act_fwd(int n_edge, int H, const float* pq, int pq_ld, const float* r, const float* d0,
+                              const float* w_rd, const int* edge_i, const int* edge_j, float* a, void* stream);
+int geoldm_train_edge_act_bwd(int n_edge, int H, const float* pq, int pq_ld, const float* r, const float* d0,
+                              const float* w_rd, const int* edge_i, const int* edge_j, const float* da, float* dpq,
+                              float* dr, float* dd0, float* dw_rd, void* stream);
+int geoldm_train_edge_tail_fwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
+                               int gate, int attention, const int* edge_i, float div, float* agg, float* sc,
+                               void* stream);
+int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
+                               int gate, int attention, const int* edge_i, float div, const float* dagg, const float* dsc,
+                               float* dmpre, float* db2, float* dw, float* dbw, void* stream);
 /* ---- evaluation side: bond-order stability of a ragged batch of molecules.
  * Replaces the Python double loop of qm9/analyze.py:209-245 (check_stability) + qm9/bond_analyze.py:101-146.
  * x [N][3] fp32, atom_type [N] in [0, n_types), mol_off [n_mol+1]; thr [3][n_types][n_types] = single/double/triple
