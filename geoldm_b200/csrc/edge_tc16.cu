@@ -37,9 +37,10 @@ constexpr int TM = 128;          // rows per tile (TMEM lanes)
 constexpr int BK = 64;           // k-slab: 64 fp16 = 128 bytes per row = one swizzle row
 constexpr int NWS = 3;           // W pipeline stages
 // Warp roles per mode.  The A generator is latency bound (two dependent global-load phases per k-slab and thread), so
-// the modes with a light fused tail (EQUIV, DENSE, RAW) run 16 producer warps (2 rows x 8 columns per thread and slab,
-// one load phase) and 4 epilogue warps (one per TMEM lane quarter, all H columns each); GCL keeps 8 + 8 because its
-// tail (second SiLU, gate, segment sum) is as long as its A generation.
+// EQUIV, DENSE and RAW run 16 producer warps (2 rows x 8 columns per thread and slab, one load phase) next to the 8
+// epilogue warps (832 threads, 72 registers); GCL keeps 8 + 8 (576 threads, 96 registers): its tail (second SiLU, gate,
+// segment sum) is as long as its A generation and its 4-row producers spill at 72 registers (measured slower).
+// Epilogue warp w owns TMEM lanes 32 (w % 4) .. +31 (= tile rows) and column half w / 4.
 template <int MODE>
 struct Roles {
   static constexpr int EPI_W = 8;
@@ -53,7 +54,7 @@ struct Roles {
 };
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
 constexpr uint32_t PACK_HDR = 128;   // bytes: float inv_scale at offset 0
-constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;   // see edge_tc.cu; re-measured for kind::f16 with scripts/tc_bias_probe.py
+constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;   // see edge_tc.cu (round-toward-zero accumulation of the tensor core)
 
 struct Args {
   int n_tile, n_rows;
