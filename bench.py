@@ -376,8 +376,11 @@ def main():
         launches_per_step = egnn_launches + 1 + 1 + 2 + 1 + 1   # + prep, nan-flag fill, finish a/b, update, advance
         line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if mode == "fp32" else mode, "data": "synthetic", "config": workload_config(n_gpus),
-                "mma_mode": mode, "edge_msgs_per_s": 18.0 * tot_edges / (ms_per_step * 1e-3),
+                "dtype": "f32", "data": "synthetic", "config": workload_config(n_gpus),
+                "mma_mode": mode, "arithmetic": {"fp32": "fp32 FFMA", "3xtf32": "fp32-equivalent products from 3 tf32 MMAs, fp32 accumulate",
+                                                  "3xf16": "fp32-equivalent products from 3 fp16 MMAs (hi/lo split operands), fp32 accumulate",
+                                                  "tf32": "single tf32 MMA (fails the 1e-5 gate)"}.get(mode, mode),
+                "edge_msgs_per_s": 18.0 * tot_edges / (ms_per_step * 1e-3),
                 "finite": finite, "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K,
                 "roofline": {"bound": "tensor", "kernel": "fused GCL edge kernel (geoldm_edge_gcl), rank 0 shard",
                              "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
