@@ -25,7 +25,7 @@ def _draws(seed, T, bs, n, latent):
 
 def test_model_sample_chain():
     cfg, sd, a, _ = load_golden("chain_model")
-    model = build_cuda_model(cfg, sd, "cuda", "3xtf32")
+    model = build_cuda_model(cfg, sd, "cuda", "3xf16")
     nodes = a["nodes"].tolist()
     kf = int(a["keep_frames"][0])
     nm, em = O.build_masks(nodes, 12)
@@ -42,7 +42,7 @@ def test_model_sample_chain():
 def test_sampling_sample_chain():
     from geoldm_b200.sampling import sample_chain
     cfg, sd, a, meta = load_golden("chain_sampling")
-    model = build_cuda_model(cfg, sd, "cuda", "3xtf32")
+    model = build_cuda_model(cfg, sd, "cuda", "3xf16")
     args = make_args(cfg)
     info = {"name": "qm9", "atom_decoder": ['H', 'C', 'N', 'O', 'F'], "max_n_nodes": 29}
     noise = _draws(int(a["torch_seed"][0]), cfg.diffusion_steps, 1, 19, cfg.latent_nf)
@@ -57,7 +57,7 @@ def test_sampling_sample_chain():
 def test_sweep_conditional_fix_noise():
     from geoldm_b200.sampling import sample_sweep_conditional
     cfg, sd, a, meta = load_golden("chain_sweep")
-    model = build_cuda_model(cfg, sd, "cuda", "3xtf32")
+    model = build_cuda_model(cfg, sd, "cuda", "3xf16")
     args = make_args(cfg)
     args.dataset = "qm9_second_half"
     info = {"name": "qm9_second_half", "atom_decoder": ['H', 'C', 'N', 'O', 'F'], "max_n_nodes": 29}
