@@ -33,7 +33,8 @@ def load_model(model, path):
 
 def load_checkpoint(model_path, device, dataset_info, mma_mode="3xf16", use_ema=None):
     """-> (generative_model, nodes_dist, prop_dist, args).  ``dataset_info`` is the reference's
-    configs/datasets_config.py entry for args.dataset (atom_decoder, n_nodes histogram, max_n_nodes)."""
+    configs/datasets_config.py entry for args.dataset (atom_decoder, n_nodes histogram, max_n_nodes).
+    Both files are Python pickles (the reference's format): load experiment directories from trusted sources only."""
     with open(join(model_path, 'args.pickle'), 'rb') as f:
         args = pickle.load(f)
     if not hasattr(args, 'normalization_factor'):
