@@ -13,6 +13,18 @@ def build_masks(nodesxsample, max_n_nodes, device):
     return node_mask.unsqueeze(2), edge_mask.reshape(-1, 1)
 
 
+def check_sample_invariants(x, one_hot, charges, node_mask, include_charges):
+    """The reference's post-sampling asserts (qm9/sampling.py:141-150, equivariant_diffusion/utils.py:46-56): padded
+    entries are zero and the coordinates of every molecule are centred.  Evaluated on the device with ONE host read."""
+    pad = 1 - node_mask
+    worst_pad = torch.stack([(x * pad).abs().max(), (one_hot.to(x.dtype) * pad).abs().max(),
+                             (charges.to(x.dtype) * pad).abs().max() if include_charges and charges.numel() else x.new_zeros(())])
+    rel_mean = x.sum(dim=1, keepdim=True).abs().max() / (x.abs().max() + 1e-10)
+    stats = torch.cat([worst_pad, rel_mean.reshape(1)]).cpu()
+    assert float(stats[:3].max()) < 1e-4, 'Variables not masked properly.'
+    assert float(stats[3]) < 1e-2, f'Mean is not zero, relative_error {float(stats[3])}'
+
+
 def sample(args, device, generative_model, dataset_info, prop_dist=None, nodesxsample=torch.tensor([10]),
            context=None, fix_noise=False, **sampler_kwargs):
     max_n_nodes = dataset_info['max_n_nodes']
@@ -29,6 +41,7 @@ def sample(args, device, generative_model, dataset_info, prop_dist=None, nodesxs
         raise ValueError(args.probabilistic_model)
     x, h = generative_model.sample(batch_size, max_n_nodes, node_mask, edge_mask, context, fix_noise=fix_noise,
                                    **sampler_kwargs)
+    check_sample_invariants(x, h['categorical'], h['integer'], node_mask, args.include_charges)
     return h['categorical'], h['integer'], x, node_mask
 
 
