@@ -496,3 +496,33 @@ def test_f16_split_saturates_instead_of_nan(dev):
     ok = torch.ones(m, dtype=torch.bool)
     ok[5] = ok[9] = False
     assert O.err_metric(out[ok].double(), ref[ok]) < 5e-6          # rows without out-of-range entries are unaffected
+
+
+@pytest.mark.parametrize("mode", ["fp32", "3xf16"])
+@pytest.mark.parametrize("nodes", [[1, 1, 1], [1, 2, 1, 3], [2], [29, 1]])
+def test_degenerate_molecules_vs_oracle(dev, mode, nodes):
+    """Single atoms (no edges at all), pairs, and mixtures: the ragged path must reproduce the padded reference maths
+    (an isolated atom only goes through the node MLPs; its velocity is exactly zero after the CoM projection)."""
+    if mode != "fp32" and not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    cfg = O.OracleConfig(nf=64, n_layers=2)
+    sd = O.make_state_dict(cfg, 21)
+    model = build_cuda_model(cfg, sd, dev, mode)
+    n_max = max(nodes)
+    nm, em = O.build_masks(nodes, n_max)
+    g = torch.Generator().manual_seed(len(nodes))
+    z = torch.randn(len(nodes), n_max, 3 + cfg.latent_nf, generator=g) * nm
+    z = torch.cat([O.remove_mean_with_mask(z[..., :3], nm), z[..., 3:]], 2)
+    t = torch.rand(len(nodes), 1, generator=g)
+    out = model.dynamics._forward(t.to(dev), z.to(dev), nm.to(dev), em.to(dev), None).cpu()
+    with torch.no_grad():
+        ref = O.dynamics_forward(O.cast_state_dict(sd, torch.float64), cfg, t.double(), z.double(), nm.double(),
+                                 em.double(), None)
+    assert torch.isfinite(out).all()
+    eh = O.err_metric(out[..., 3:], ref[..., 3:])
+    ex = float((out[..., :3].double() - ref[..., :3]).abs().max())
+    print(f"[degenerate] nodes={nodes} mode={mode}: h err {eh:.2e}, x abs err {ex:.2e}")
+    assert eh < FWD_TOL and ex < 1e-6
+    for b, n in enumerate(nodes):
+        if n == 1:
+            assert float(out[b, :, :3].abs().max()) == 0.0
