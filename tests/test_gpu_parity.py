@@ -526,3 +526,29 @@ def test_degenerate_molecules_vs_oracle(dev, mode, nodes):
     for b, n in enumerate(nodes):
         if n == 1:
             assert float(out[b, :, :3].abs().max()) == 0.0
+
+
+def test_full_size_properties_1250_molecules(dev):
+    """BASELINE configs[2] size (1250 QM9 molecules per GPU, nf=256, 9 blocks) in the default 3xf16 mode, through
+    size-independent properties: rotation equivariance, invariance to the order of the molecules in the batch, CoM-free
+    velocities, padded entries exactly zero, run-to-run determinism."""
+    if not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    cfg, sd, model, nodes, nm, em, z = _config1(dev, mode="3xf16", bs=1250, seed=3)
+    t = torch.randint(0, 1001, (len(nodes), 1)).float() / 1000
+    fwd = lambda zz, tt, m1, m2: model.dynamics._forward(tt.to(dev), zz.to(dev), m1.to(dev), m2.to(dev), None).cpu()
+    out = fwd(z, t, nm, em)
+    assert torch.isfinite(out).all() and torch.equal(out, fwd(z, t, nm, em))
+    assert float((out * (1 - nm)).abs().max()) == 0.0
+    assert float(out[..., :3].sum(1).abs().max()) < 1e-4
+    q, _ = torch.linalg.qr(torch.randn(3, 3))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    outr = fwd(torch.cat([z[..., :3] @ q.T, z[..., 3:]], 2), t, nm, em)
+    e_x, e_h = O.err_metric(outr[..., :3], out[..., :3] @ q.T), O.err_metric(outr[..., 3:], out[..., 3:])
+    perm = torch.randperm(len(nodes))
+    nmp, emp = O.build_masks([nodes[i] for i in perm.tolist()], 29)
+    outp = fwd(z[perm], t[perm], nmp, emp)
+    e_p = O.err_metric(outp, out[perm])
+    print(f"[1250 molecules, 3xf16] rotation: x {e_x:.2e} h {e_h:.2e}; molecule permutation {e_p:.2e}")
+    assert e_x < 2e-5 and e_h < 5e-6 and e_p < 5e-6
