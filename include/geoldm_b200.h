@@ -114,6 +114,8 @@ const char* geoldm_last_error(void);
 int geoldm_has_tcgen05(void);
 
 /* ---- whole-network entry point: EGNN.forward (egnn/egnn_new.py:184-197) ------------------- */
+/* bytes of caller-owned scratch for a batch of n_node atoms and n_edge directed edges: node buffers (h, t1, agg, the
+ * [N][4H] projections, coordinates) plus two [E] arrays of squared distances (ABI v2; v1 took n_node only) */
 size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node, int n_edge);
 int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights* w, const geoldm_batch* b,
                         const float* h_in,  /* [N][in_node_nf] */
