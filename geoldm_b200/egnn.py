@@ -116,6 +116,8 @@ class EGNN(nn.Module):
         self.normalization_factor, self.aggregation_method = normalization_factor, aggregation_method
         self.attention, self.tanh = attention, tanh
         self.sin_embedding = None
+        if mma_mode == "auto":      # fastest parity-green arithmetic this hidden size supports (tensor-core tiles need
+            mma_mode = "3xf16" if (hidden_nf % 64 == 0 and hidden_nf <= 256) else "fp32"   # H in {64, 128, 192, 256})
         self.mma_mode = mma_mode
         self.embedding = nn.Linear(in_node_nf, hidden_nf)
         self.embedding_out = nn.Linear(hidden_nf, self.out_node_nf)

@@ -31,7 +31,7 @@ def load_model(model, path):
     return model
 
 
-def load_checkpoint(model_path, device, dataset_info, mma_mode="3xf16", use_ema=None):
+def load_checkpoint(model_path, device, dataset_info, mma_mode="auto", use_ema=None):
     """-> (generative_model, nodes_dist, prop_dist, args).  ``dataset_info`` is the reference's
     configs/datasets_config.py entry for args.dataset (atom_decoder, n_nodes histogram, max_n_nodes).
     Both files are Python pickles (the reference's format): load experiment directories from trusted sources only."""

@@ -1,8 +1,9 @@
 """Model factory with the reference's surface (qm9/models.py): ``get_latent_diffusion(args, device,
 dataset_info, dataloader_train) -> (model, nodes_dist, prop_dist)`` (:103-166), ``get_autoencoder`` (:54-100)
 and ``DistributionNodes`` (:178-215).  ``args`` is the same argparse Namespace the reference uses; the extra
-optional attribute ``args.mma_mode`` ("fp32" | "3xf16" | "3xtf32" | "tf32") selects the arithmetic of the
-fused kernels."""
+optional attribute ``args.mma_mode`` ("auto" | "fp32" | "3xf16" | "3xtf32" | "tf32") selects the arithmetic of the
+fused kernels; the default "auto" picks the fp16-split tensor-core path when hidden_nf is 64/128/192/256 and the fp32
+FFMA path otherwise."""
 from __future__ import annotations
 
 import numpy as np
@@ -37,7 +38,7 @@ def _egnn_kwargs(args, device):
     return dict(n_dims=3, device=device, hidden_nf=args.nf, act_fn=torch.nn.SiLU(), attention=args.attention,
                 tanh=args.tanh, mode=args.model, norm_constant=args.norm_constant, inv_sublayers=args.inv_sublayers,
                 sin_embedding=args.sin_embedding, normalization_factor=args.normalization_factor,
-                aggregation_method=args.aggregation_method, mma_mode=getattr(args, "mma_mode", "fp32"))
+                aggregation_method=args.aggregation_method, mma_mode=getattr(args, "mma_mode", "auto"))
 
 
 def get_autoencoder(args, device, dataset_info, dataloader_train):
