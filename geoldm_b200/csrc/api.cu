@@ -18,6 +18,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct Workspace {
   float *h, *h2, *t1, *agg, *pq, *xa, *xb, *xagg, *dx;
   float *r_edge, *d0_edge;   // [E] squared distances of the current / entry coordinates (tensor-core edge kernels)
+  float *u_edge;             // [E][4] normalised coordinate differences of the current coordinates
   size_t bytes;
 };
 static Workspace carve(void* base, int n_node, int n_edge, int H) {
@@ -31,19 +32,20 @@ static Workspace carve(void* base, int n_node, int n_edge, int H) {
   const size_t nh = (size_t)n_node * H;
   w.h = take(nh); w.h2 = take(nh); w.t1 = take(nh); w.agg = take(nh); w.pq = take(4 * nh);
   w.xa = take((size_t)3 * n_node); w.xb = take((size_t)3 * n_node); w.xagg = take((size_t)3 * n_node); w.dx = take((size_t)3 * n_node);
-  w.r_edge = take((size_t)n_edge); w.d0_edge = take((size_t)n_edge);
+  w.r_edge = take((size_t)n_edge); w.d0_edge = take((size_t)n_edge); w.u_edge = take((size_t)4 * n_edge);
   w.bytes = off;
   return w;
 }
 
 static int edge_dispatch(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                          const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st,
-                         const float* r_edge = nullptr, const float* d0_edge = nullptr) {
+                         const float* r_edge = nullptr, const float* d0_edge = nullptr, const float* u_edge = nullptr) {
   if (cfg.mma_mode == GEOLDM_MMA_FP32_SIMT) {
     GEOLDM_REQUIRE(pq_ld == 2 * cfg.hidden_nf, "edge_simt expects a [N][2H] projection buffer");
     return launch_edge_simt(cfg, w, b, equiv, pq, x, x0, out, st);
   }
-  if (cfg.mma_mode == GEOLDM_MMA_3XF16) return launch_edge_tc16(cfg, w, b, equiv, pq, pq_ld, x, x0, r_edge, d0_edge, out, st);
+  if (cfg.mma_mode == GEOLDM_MMA_3XF16)
+    return launch_edge_tc16(cfg, w, b, equiv, pq, pq_ld, x, x0, r_edge, d0_edge, u_edge, out, st);
   return launch_edge_tc(cfg, w, b, equiv, pq, pq_ld, x, x0, out, st);
 }
 }  // namespace geoldm
@@ -97,12 +99,13 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   const bool pre_dist = cfg->mma_mode == GEOLDM_MMA_3XF16;
   const float* r_edge = pre_dist ? ws.r_edge : nullptr;
   const float* d0_edge = pre_dist ? ws.d0_edge : nullptr;
-  if (pre_dist && (rc = launch_edge_dist(*b, x_in, ws.d0_edge, st))) return rc;
+  const float* u_edge = pre_dist ? ws.u_edge : nullptr;
+  if (pre_dist && (rc = launch_edge_dist(*b, x_in, ws.d0_edge, ws.u_edge, cfg->norm_constant, st))) return rc;
   for (int l = 0; l < cfg->n_layers; ++l) {
     const geoldm_block& blk = w->block[l];
     if (pre_dist) {
       if (l == 0) r_edge = ws.d0_edge;                    // x == x_in in the first block
-      else { if ((rc = launch_edge_dist(*b, x_cur, ws.r_edge, st))) return rc; r_edge = ws.r_edge; }
+      else { if ((rc = launch_edge_dist(*b, x_cur, ws.r_edge, ws.u_edge, cfg->norm_constant, st))) return rc; r_edge = ws.r_edge; }
     }
     for (int s = 0; s < cfg->inv_sublayers; ++s) {
       const geoldm_gcl& g = blk.gcl[s];
@@ -140,7 +143,7 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
       if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
     }
     cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
-    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, pq_ld, x_cur, x_in, ws.xagg, st, r_edge, d0_edge))) return rc;
+    if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, pq_ld, x_cur, x_in, ws.xagg, st, r_edge, d0_edge, u_edge))) return rc;
     const bool last = (l + 1 == cfg->n_layers);
     float* x_next = last ? x_out : x_bufs[xi];
     float* dx_next = (last && dx_out) ? dx_out : ws.dx;   // dx is updated in place (elementwise)

@@ -46,6 +46,80 @@ __device__ __forceinline__ float silu(float v) {
 }
 __device__ __forceinline__ float sigmoidf_(float v) { return rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f)); }
 
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot) -------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// SiLU of four values held as two packed pairs, in place: 1.5 MUFU operations per value instead of 2.
+//   d = 1 + 2^(-v log2 e);  the reciprocals of the lane-wise partners share one rcp:  r = 1 / (dA dB),
+//   1/dA = r dB, 1/dB = r dA.   The exponent is clamped at 60 so that dA dB <= 2^121 stays finite; for v < -41.6
+//   sigmoid(v) is then 2^-60 instead of e^v (absolute error of SiLU < 1e-16 |v|).  SiLU(0) = 0 exactly; a NaN in one
+//   value does not reach its partner (min() drops it before the product).  Error: <= ~3 ulp, like ex2 + rcp per value.
+__device__ __forceinline__ void silu_x4(f32x2& A, f32x2& B) {
+  const f32x2 nl2e = pk2(-1.4426950408889634f, -1.4426950408889634f);
+  const f32x2 one = pk2(1.0f, 1.0f);
+  float a0, a1, b0, b1;
+  upk2(mul2(A, nl2e), a0, a1);
+  upk2(mul2(B, nl2e), b0, b1);
+  a0 = ex2_ftz(fminf(a0, 60.0f)); a1 = ex2_ftz(fminf(a1, 60.0f));
+  b0 = ex2_ftz(fminf(b0, 60.0f)); b1 = ex2_ftz(fminf(b1, 60.0f));
+  const f32x2 dA = add2(pk2(a0, a1), one), dB = add2(pk2(b0, b1), one);
+  float p0, p1;
+  upk2(mul2(dA, dB), p0, p1);
+  const f32x2 r = pk2(rcp_ftz(p0), rcp_ftz(p1));
+  A = mul2(A, mul2(r, dB));
+  B = mul2(B, mul2(r, dA));
+}
+
+// SiLU of eight values (four packed pairs), ONE reciprocal per four values: 1.25 MUFU operations per value.
+//   r = 1 / (dA dB dC dD); 1/dA = r (dC dD) dB, ...   Exponent clamped at 30 (product <= 2^121): for v < -20.8
+//   sigmoid(v) reads 2^-30 instead of e^v, absolute error of SiLU < 1e-9 |v|.
+__device__ __forceinline__ void silu_x8(f32x2& A, f32x2& B, f32x2& C, f32x2& D) {
+  const f32x2 nl2e = pk2(-1.4426950408889634f, -1.4426950408889634f);
+  const f32x2 one = pk2(1.0f, 1.0f);
+  float a0, a1, b0, b1, c0, c1, d0, d1;
+  upk2(mul2(A, nl2e), a0, a1);
+  upk2(mul2(B, nl2e), b0, b1);
+  upk2(mul2(C, nl2e), c0, c1);
+  upk2(mul2(D, nl2e), d0, d1);
+  a0 = ex2_ftz(fminf(a0, 30.0f)); a1 = ex2_ftz(fminf(a1, 30.0f));
+  b0 = ex2_ftz(fminf(b0, 30.0f)); b1 = ex2_ftz(fminf(b1, 30.0f));
+  c0 = ex2_ftz(fminf(c0, 30.0f)); c1 = ex2_ftz(fminf(c1, 30.0f));
+  d0 = ex2_ftz(fminf(d0, 30.0f)); d1 = ex2_ftz(fminf(d1, 30.0f));
+  const f32x2 dA = add2(pk2(a0, a1), one), dB = add2(pk2(b0, b1), one);
+  const f32x2 dC = add2(pk2(c0, c1), one), dD = add2(pk2(d0, d1), one);
+  const f32x2 pAB = mul2(dA, dB), pCD = mul2(dC, dD);
+  float p0, p1;
+  upk2(mul2(pAB, pCD), p0, p1);
+  const f32x2 r = pk2(rcp_ftz(p0), rcp_ftz(p1));
+  const f32x2 rAB = mul2(r, pCD), rCD = mul2(r, pAB);
+  A = mul2(A, mul2(rAB, dB));
+  B = mul2(B, mul2(rAB, dA));
+  C = mul2(C, mul2(rCD, dD));
+  D = mul2(D, mul2(rCD, dC));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -100,9 +174,11 @@ int launch_tc_selftest(int H, int terms, const float* pq, const int* edge_i, con
 // fp16-split variants (edge_tc16.cu), selected by terms == 16 / GEOLDM_MMA_3XF16
 int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                      const float* pq, int pq_ld, const float* x, const float* x0, const float* r_edge,
-                     const float* d0_edge, float* out, cudaStream_t st);
-// out[e] = |x_i - x_j|^2 for every packed edge (same association as edge_geom)
-int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, cudaStream_t st);
+                     const float* d0_edge, const float* u_edge, float* out, cudaStream_t st);
+// out[e] = |x_i - x_j|^2 for every packed edge (same association as edge_geom); u_out (optional, [E][4]) receives the
+// normalised difference (x_i - x_j) / (sqrt(r + 1e-8) + norm_constant) of coord2diff (egnn_new.py:249-255)
+int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, float* u_out, float norm_constant,
+                     cudaStream_t st);
 int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
                        int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st);
 int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,

@@ -769,7 +769,7 @@ int launch_h(int H, const TcArgs& a, cudaStream_t st) {
 
 int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                    const float* pq, int pq_ld, const float* x, const float* x0, float* out, cudaStream_t st) {
-  if (cfg.mma_mode == GEOLDM_MMA_3XF16) return launch_edge_tc16(cfg, w, b, equiv, pq, pq_ld, x, x0, nullptr, nullptr, out, st);
+  if (cfg.mma_mode == GEOLDM_MMA_3XF16) return launch_edge_tc16(cfg, w, b, equiv, pq, pq_ld, x, x0, nullptr, nullptr, nullptr, out, st);
   GEOLDM_REQUIRE(b.tile_m == TM, "edge_tc: batch tile_m=%d, kernel needs %d", b.tile_m, TM);
   GEOLDM_REQUIRE(w.tc_pack != nullptr, "edge_tc: tc_pack missing (weights not packed for the tensor-core path)");
   GEOLDM_REQUIRE(equiv || !cfg.attention || w.b_out != nullptr, "edge_tc: attention needs b_out");

@@ -43,13 +43,15 @@ constexpr int NWS = 3;           // W pipeline stages
 // Epilogue warp w owns TMEM lanes 32 (w % 4) .. +31 (= tile rows) and column half w / 4.
 template <int MODE>
 struct Roles {
+#ifndef GEOLDM_GCL_PROD_W
+#define GEOLDM_GCL_PROD_W 8
+#endif
   static constexpr int EPI_W = 8;
-  static constexpr int PROD_W = (MODE == 0) ? 8 : 16;
+  static constexpr int PROD_W = (MODE == 0) ? GEOLDM_GCL_PROD_W : 16;
   static constexpr int WARP_LOAD = EPI_W + PROD_W, WARP_MMA = WARP_LOAD + 1;
   static constexpr int NTHREADS = 32 * (EPI_W + PROD_W + 2);
   static constexpr int EPI_T = 32 * EPI_W;
-  static constexpr int ROW_STEP = 4 * PROD_W;                 // producer thread (rbase, chunk) owns rows rbase + ROW_STEP p
-  static constexpr int ROWS_PT = 128 / ROW_STEP;              // 4 or 2
+  static constexpr int ROWS_PT = 128 / (4 * PROD_W);          // consecutive tile rows per producer thread: 4 or 2
   static constexpr int NHALF = EPI_W / 4;                     // column halves split over distinct epilogue warps
 };
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
@@ -66,6 +68,7 @@ struct Args {
   const int* edge_i; const int* edge_j;
   const float* w_rd;
   const float* r_edge; const float* d0_edge;   // [E] precomputed squared distances (or null: computed from x / x0)
+  const float4* u_edge;                        // [E] precomputed (x_i - x_j) / (|x_i - x_j| + c) (or null)
   const float* a1; const float* a2; int k1, k2; float a2_div;
   const uint8_t* w_pack;    // header + [block][slab][N-half][hi image | lo image]
   const float* b2; const float* w_out; const float* b_out; const float* res;
@@ -93,7 +96,8 @@ struct Smem {
   static constexpr uint32_t OFF_DX = OFF_PS + 8 * 34 * 4;
   static constexpr uint32_t OFF_DOT = OFF_DX + TM * 16;
   static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;
-  static constexpr uint32_t OFF_BAR = OFF_VEC + 2 * H * 4;
+  static constexpr uint32_t OFF_WRD = OFF_VEC + 2 * H * 4;    // float [2][H]: distance columns of the first edge layer
+  static constexpr uint32_t OFF_BAR = OFF_WRD + 2 * H * 4;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + (3 * NWS + 2 * NAS + 4) * 8;
   static constexpr uint32_t BYTES = OFF_TMEM + 16;
   static constexpr uint32_t ALLOC = BYTES + 1024;
@@ -135,12 +139,24 @@ __device__ __forceinline__ void split_f16x8(const float (&e)[8], uint4& hi, uint
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// packed pair -> fp16x2 hi and fp16x2 lo (lo = fp16(v - hi), exact subtraction)
+__device__ __forceinline__ void split_f16x2(f32x2 e, uint32_t& hi, uint32_t& lo) {
+  float e0, e1;
+  upk2(e, e0, e1);
+  hi = pack_f16x2_sat(e0, e1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(e), "l"(pk2(hf.x, hf.y)));
+  upk2(d, e0, e1);
+  lo = pack_f16x2_sat(e0, e1);
+}
+
 template <int H, int MODE>
 __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Args a) {
   using S = Smem<H, MODE>;
   using R = Roles<MODE>;
   constexpr int NTHREADS = R::NTHREADS, EPI_T = R::EPI_T, WARP_LOAD = R::WARP_LOAD, WARP_MMA = R::WARP_MMA;
-  constexpr int ROWS_PT = R::ROWS_PT, ROW_STEP = R::ROW_STEP, NHALF = R::NHALF;
+  constexpr int ROWS_PT = R::ROWS_PT, NHALF = R::NHALF;
   constexpr int NAS = S::NAS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -175,7 +191,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
   if (warp == WARP_MMA) tmem_alloc2(tmem_slot, 512);
   if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
     float* vec = reinterpret_cast<float*>(smem + S::OFF_VEC);
-    for (int c = tid; c < H; c += NTHREADS) { vec[c] = a.b2[c]; vec[H + c] = a.w_out[c]; }
+    float* wrd = reinterpret_cast<float*>(smem + S::OFF_WRD);
+    for (int c = tid; c < H; c += NTHREADS) { vec[c] = a.b2[c]; vec[H + c] = a.w_out[c]; wrd[c] = a.w_rd[c]; wrd[H + c] = a.w_rd[H + c]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -189,8 +206,13 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
 
   auto tile_of = [&](int iter, int& tile, int& nb, int& row0, int& nrows) {
     const int work = iter * n_workers + worker;
-    nb = work / work_per_block;
-    tile = 2 * (work % work_per_block) + (int)crank;
+    if (MODE == MODE_GCL || MODE == MODE_EQUIV) {      // edge launches have one column block: no division
+      nb = 0;
+      tile = 2 * work + (int)crank;
+    } else {
+      nb = work / work_per_block;
+      tile = 2 * (work % work_per_block) + (int)crank;
+    }
     if (nb >= a.n_blocks || tile >= a.n_tile) {
       nb = nb >= a.n_blocks ? a.n_blocks - 1 : nb;
       row0 = 0; nrows = 0;
@@ -276,10 +298,13 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       })
     }
   } else if (warp >= R::EPI_W) {
-    // =========================== A producers (256 threads) ================================================
+    // =========================== A producers ==============================================================
+    // thread (rg, chunk): ROWS_PT CONSECUTIVE tile rows rg * ROWS_PT + p and the 16-byte chunk k = 8 chunk .. +7 of every
+    // k-slab.  Edge rows are sorted by (molecule, receiver, sender), so consecutive rows share the receiver: its
+    // projection P_i stays in registers across the run and is re-read only where the receiver changes.
     const int pt = tid - EPI_T;
-    const int chunk = pt & 7;        // 16-byte chunk: k = 8*chunk .. 8*chunk+7 inside the slab
-    const int rbase = pt >> 3;       // rows rbase + ROW_STEP p
+    const int chunk = pt & 7;
+    const int rg = pt >> 3;
     uint32_t it = 0;
     TC_PROF(long long tp_wait = 0; long long tp_comp = 0; long long tp_fence = 0; long long tp_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
@@ -289,27 +314,32 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       const float* pP[ROWS_PT];
       const float* pQ[ROWS_PT];
       float rr[ROWS_PT], dd[ROWS_PT];
-      bool valid[ROWS_PT];
+      unsigned lmask = 0;                  // row needs a fresh P load (first row of the thread / receiver changed)
+      int prev_i = -1;
+      // rows beyond the end of the tile are CLAMPED to its last row (an empty tile: row 0 of the launch): they produce
+      // a copy of a real row, which the epilogue ignores (accumulator rows are independent) -> no validity branches,
+      // every load unconditional and in bounds
+      const int rlast = nrows > 0 ? nrows - 1 : 0;
+      const int rbase0 = nrows > 0 ? row0 : 0;
 #pragma unroll
       for (int p = 0; p < ROWS_PT; ++p) {
-        const int r = rbase + ROW_STEP * p;
-        valid[p] = r < nrows;
-        pP[p] = nullptr; pQ[p] = nullptr; rr[p] = 0.f; dd[p] = 0.f;
-        if (valid[p]) {
-          if (MODE == MODE_DENSE) {
-            pP[p] = a.a1 + (size_t)(row0 + r) * a.k1 + 8 * chunk;
-            pQ[p] = a.a2 ? a.a2 + (size_t)(row0 + r) * a.k2 + 8 * chunk : nullptr;
-          } else {
-            const int i = a.edge_i[row0 + r];
-            pP[p] = a.pq + (size_t)i * a.pq_ld + 8 * chunk;
-            if (MODE != MODE_RAW) {
-              const int j = a.edge_j[row0 + r];
-              pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 8 * chunk;
-              if (a.r_edge) {
-                rr[p] = __ldg(a.r_edge + row0 + r);
-                dd[p] = __ldg(a.d0_edge + row0 + r);
-                continue;
-              }
+        const int grow = rbase0 + min(rg * ROWS_PT + p, rlast);
+        rr[p] = 0.f; dd[p] = 0.f; pQ[p] = nullptr;
+        if (MODE == MODE_DENSE) {
+          pP[p] = a.a1 + (size_t)grow * a.k1 + 8 * chunk;
+          pQ[p] = a.a2 ? a.a2 + (size_t)grow * a.k2 + 8 * chunk : nullptr;
+        } else {
+          const int i = a.edge_i[grow];
+          pP[p] = a.pq + (size_t)i * a.pq_ld + 8 * chunk;
+          if (i != prev_i) lmask |= 1u << p;
+          prev_i = i;
+          if (MODE != MODE_RAW) {
+            const int j = a.edge_j[grow];
+            pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 8 * chunk;
+            if (a.r_edge) {
+              rr[p] = __ldg(a.r_edge + grow);
+              dd[p] = __ldg(a.d0_edge + grow);
+            } else {
               const float* xi = a.x + 3 * (size_t)i;
               const float* xj = a.x + 3 * (size_t)j;
               const float* yi = a.x0 + 3 * (size_t)i;
@@ -319,6 +349,22 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               rr[p] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
               dd[p] = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
             }
+          }
+        }
+      }
+      if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+        // the per-row tables of this CTA's NEXT tile (streamed once, so never in L1 by themselves): requested now, they
+        // arrive while this tile is produced and the dependent index -> P/Q address chain starts from L1 hits
+        const int ntile = 2 * ((iter + 1) * n_workers + worker) + (int)crank;
+        const int n2tile = ntile + 2 * n_workers;
+        if (a.tile_row && n2tile < a.n_tile && pt == 0) prefetch_l1(a.tile_row + n2tile);   // tile_row two tiles ahead
+        if (iter + 1 < n_iter && ntile < a.n_tile && chunk == 0) {
+          const int nrow = (a.tile_row ? a.tile_row[ntile] : ntile * TM) + rg * ROWS_PT;
+          if (nrow < a.n_rows) {
+            prefetch_l1(a.edge_i + nrow);
+            prefetch_l1(a.edge_j + nrow);
+            if (a.r_edge) { prefetch_l1(a.r_edge + nrow); prefetch_l1(a.d0_edge + nrow); }
+            if (MODE == MODE_EQUIV && a.u_edge) prefetch_l1(a.u_edge + nrow);
           }
         }
       }
@@ -332,31 +378,79 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         const int st = it % NAS;
         const int k0 = s * BK;
         TC_PROF(const long long tp0 = clock64(); long long tp1 = tp0;)
-        float wr[8], wd[8];
-        if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 8 * chunk));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.w_rd + k0 + 8 * chunk + 4));
-          const float4 d0 = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 8 * chunk));
-          const float4 d1 = __ldg(reinterpret_cast<const float4*>(a.w_rd + H + k0 + 8 * chunk + 4));
-          wr[0] = r0.x; wr[1] = r0.y; wr[2] = r0.z; wr[3] = r0.w; wr[4] = r1.x; wr[5] = r1.y; wr[6] = r1.z; wr[7] = r1.w;
-          wd[0] = d0.x; wd[1] = d0.y; wd[2] = d0.z; wd[3] = d0.w; wd[4] = d1.x; wd[5] = d1.y; wd[6] = d1.z; wd[7] = d1.w;
-          if (s + 1 < n_slabs_p) {
-#pragma unroll
-            for (int p = 0; p < ROWS_PT; ++p)
-              if (valid[p]) { prefetch_l1(pP[p] + k0 + BK); prefetch_l1(pQ[p] + k0 + BK); }
-          }
-        }
         bool waited = false;
         const uint32_t a_hi = sbase + S::OFF_A + st * S::A_STAGE;
         const uint32_t a_lo = a_hi + TM * 128;
+        if constexpr (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+          // ---- A = SiLU(P_i + Q_j + w_r r_ij + w_d d0_ij), packed fp32 pairs, shared reciprocals ---------------
+          f32x2 WR[4], WD[4];
+          {
+            const uint32_t s_wrd = sbase + S::OFF_WRD + (k0 + 8 * chunk) * 4;
+            const float4 r0 = lds128f(s_wrd), r1 = lds128f(s_wrd + 16);
+            const float4 d0 = lds128f(s_wrd + H * 4), d1 = lds128f(s_wrd + H * 4 + 16);
+            WR[0] = pk2(r0.x, r0.y); WR[1] = pk2(r0.z, r0.w); WR[2] = pk2(r1.x, r1.y); WR[3] = pk2(r1.z, r1.w);
+            WD[0] = pk2(d0.x, d0.y); WD[1] = pk2(d0.z, d0.w); WD[2] = pk2(d1.x, d1.y); WD[3] = pk2(d1.z, d1.w);
+          }
+#ifdef GEOLDM_TC16_PREFETCH
+          if (s + 1 < n_slabs_p) {
 #pragma unroll
-        for (int ph = 0; ph < ROWS_PT / 2; ++ph) {   // two rows at a time: bounds the registers held by loads in flight
-          float4 v[2][2], q[2][2];
+            for (int p = 0; p < ROWS_PT; ++p) {
+              prefetch_l1(pQ[p] + k0 + BK);
+              if ((lmask >> p) & 1u) prefetch_l1(pP[p] + k0 + BK);
+            }
+          }
+#endif
+          float4 Pc0 = make_float4(0.f, 0.f, 0.f, 0.f), Pc1 = Pc0;
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            const int p = 2 * ph + pp;
-            v[pp][0] = v[pp][1] = q[pp][0] = q[pp][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid[p]) {
+          for (int ph = 0; ph < ROWS_PT / 2; ++ph) {   // the Q rows of two tile rows in flight at a time
+            float4 q[2][2];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int p = 2 * ph + pp;
+              q[pp][0] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0));
+              q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0 + 4));
+            }
+            if (ph == 0) {
+              Pc0 = __ldg(reinterpret_cast<const float4*>(pP[0] + k0));
+              Pc1 = __ldg(reinterpret_cast<const float4*>(pP[0] + k0 + 4));
+            }
+            if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int p = 2 * ph + pp;
+              const int r = rg * ROWS_PT + p;
+              if (p > 0 && ((lmask >> p) & 1u)) {
+                Pc0 = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
+                Pc1 = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
+              }
+              uint4 hi, lo;
+              const f32x2 R2 = pk2(rr[p], rr[p]), D2 = pk2(dd[p], dd[p]);
+              f32x2 e0 = fma2(WD[0], D2, fma2(WR[0], R2, add2(pk2(Pc0.x, Pc0.y), pk2(q[pp][0].x, q[pp][0].y))));
+              f32x2 e1 = fma2(WD[1], D2, fma2(WR[1], R2, add2(pk2(Pc0.z, Pc0.w), pk2(q[pp][0].z, q[pp][0].w))));
+              f32x2 e2 = fma2(WD[2], D2, fma2(WR[2], R2, add2(pk2(Pc1.x, Pc1.y), pk2(q[pp][1].x, q[pp][1].y))));
+              f32x2 e3 = fma2(WD[3], D2, fma2(WR[3], R2, add2(pk2(Pc1.z, Pc1.w), pk2(q[pp][1].z, q[pp][1].w))));
+#ifdef GEOLDM_SILU_QUAD
+              silu_x8(e0, e1, e2, e3);
+#else
+              silu_x4(e0, e1);
+              silu_x4(e2, e3);
+#endif
+              split_f16x2(e0, hi.x, lo.x); split_f16x2(e1, hi.y, lo.y);
+              split_f16x2(e2, hi.z, lo.z); split_f16x2(e3, hi.w, lo.w);
+              const uint32_t off = sw128_off(r, chunk);
+              sts128(a_hi + off, hi);
+              sts128(a_lo + off, lo);
+            }
+          }
+        } else {
+          // ---- DENSE / RAW: plain fp32 rows -> fp16 hi | lo ------------------------------------------------------
+#pragma unroll
+          for (int ph = 0; ph < ROWS_PT / 2; ++ph) {   // two rows at a time: bounds the registers held by loads in flight
+            float4 v[2][2], q[2][2];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int p = 2 * ph + pp;
+              v[pp][0] = v[pp][1] = q[pp][0] = q[pp][1] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (MODE == MODE_DENSE) {
                 if (k0 < a.k1) {
                   v[pp][0] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
@@ -368,40 +462,32 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               } else {
                 v[pp][0] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
                 v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
-                if (MODE != MODE_RAW) {
-                  q[pp][0] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0));
-                  q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0 + 4));
+              }
+            }
+            if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int p = 2 * ph + pp;
+              const int r = rg * ROWS_PT + p;
+              const float vv[8] = {v[pp][0].x, v[pp][0].y, v[pp][0].z, v[pp][0].w, v[pp][1].x, v[pp][1].y, v[pp][1].z, v[pp][1].w};
+              const float qq[8] = {q[pp][0].x, q[pp][0].y, q[pp][0].z, q[pp][0].w, q[pp][1].x, q[pp][1].y, q[pp][1].z, q[pp][1].w};
+              float e[8];
+              if (MODE == MODE_DENSE) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  if (k0 < a.k1) e[c] = vv[c];
+                  else e[c] = (a.a2_div != 1.0f) ? __fdiv_rn(qq[c], a.a2_div) : qq[c];
                 }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) e[c] = vv[c];
               }
+              uint4 hi, lo;
+              split_f16x8(e, hi, lo);
+              const uint32_t off = sw128_off(r, chunk);
+              sts128(a_hi + off, hi);
+              sts128(a_lo + off, lo);
             }
-          }
-          if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
-#pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            const int p = 2 * ph + pp;
-            const int r = rbase + ROW_STEP * p;
-            const float vv[8] = {v[pp][0].x, v[pp][0].y, v[pp][0].z, v[pp][0].w, v[pp][1].x, v[pp][1].y, v[pp][1].z, v[pp][1].w};
-            const float qq[8] = {q[pp][0].x, q[pp][0].y, q[pp][0].z, q[pp][0].w, q[pp][1].x, q[pp][1].y, q[pp][1].z, q[pp][1].w};
-            float e[8];
-            if (MODE == MODE_GCL || MODE == MODE_EQUIV) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c)      // rows beyond the tile: v = q = 0, rr = dd = 0 -> SiLU(0) = 0 exactly
-                e[c] = silu(fmaf(wd[c], dd[p], fmaf(wr[c], rr[p], vv[c] + qq[c])));
-            } else if (MODE == MODE_DENSE) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                if (k0 < a.k1) e[c] = vv[c];
-                else e[c] = (a.a2_div != 1.0f) ? __fdiv_rn(qq[c], a.a2_div) : qq[c];
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) e[c] = vv[c];
-            }
-            uint4 hi, lo;
-            split_f16x8(e, hi, lo);
-            const uint32_t off = sw128_off(r, chunk);
-            sts128(a_hi + off, hi);
-            sts128(a_lo + off, lo);
           }
         }
         TC_PROF(const long long tp2 = clock64();)
@@ -446,8 +532,13 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         if (valid) {
           my_i = a.edge_i[row0 + r];
           if (MODE == MODE_EQUIV && hf == 0) {
-            EdgeGeom g = edge_geom(a.x, a.x0, my_i, a.edge_j[row0 + r], a.norm_constant);
-            ux = g.ux; uy = g.uy; uz = g.uz;
+            if (a.u_edge) {
+              const float4 u4 = __ldg(a.u_edge + row0 + r);
+              ux = u4.x; uy = u4.y; uz = u4.z;
+            } else {
+              EdgeGeom g = edge_geom(a.x, a.x0, my_i, a.edge_j[row0 + r], a.norm_constant);
+              ux = g.ux; uy = g.uy; uz = g.uz;
+            }
           }
         }
         if (hf == 0) sts32i(s_i + 4 * r, my_i);
@@ -459,40 +550,12 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       const uint32_t taddr = tlane + region * 256;
 
       if (MODE == MODE_DENSE || MODE == MODE_RAW) {
-        if (MODE == MODE_DENSE && a.epi == 2) {
-          // residual epilogue: row-per-lane (each thread re-reads and writes its own row; measured faster than the
-          // transposed form for this read-modify-write pattern)
-          float* orow = a.out + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC;
-          const float* rrow = (MODE == MODE_DENSE && a.epi == 2) ? a.res + (size_t)(row0 + r) * a.ldo + nb * H + hf * HC : nullptr;
-          const float* bias = (MODE == MODE_DENSE && a.b2) ? a.b2 + nb * H + hf * HC : nullptr;
-#pragma unroll 1
-          for (int cc = 0; cc < NCH; ++cc) {
-            uint32_t v[32];
-            tmem_ld32(taddr + cc * 32, v);
-            tmem_ld_wait();
-            if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }     // registers hold the last chunk
-            if (valid) {
-#pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                float o[4] = {__uint_as_float(v[c4 * 4]) * scale, __uint_as_float(v[c4 * 4 + 1]) * scale,
-                              __uint_as_float(v[c4 * 4 + 2]) * scale, __uint_as_float(v[c4 * 4 + 3]) * scale};
-                if (bias) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + c4 * 4));
-                  o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
-                }
-                if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
-                if (rrow) {
-                  const float4 rs = __ldg(reinterpret_cast<const float4*>(rrow + cc * 32 + c4 * 4));
-                  o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
-                }
-                *reinterpret_cast<float4*>(orow + cc * 32 + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-              }
-            }
-          }
-        } else {
-          // lane = accumulator row after tcgen05.ld; a row-per-lane global store would touch 32 lines per instruction, so
+        {
+          // lane = accumulator row after tcgen05.ld; a row-per-lane global access would touch 32 lines per instruction, so
           // every 32 x 32 chunk goes through this warp's transposition tile and leaves as 4 rows x 128 contiguous bytes per
-          // instruction (lane = (row % 4, 16-byte column group)), with bias / SiLU / residual applied on the way out
+          // instruction (lane = (row % 4, 16-byte column group)), with bias / SiLU / residual applied on the way out.
+          // The residual rows are requested as one batch of eight coalesced loads per chunk (one exposed L2 latency per
+          // chunk, not one per row group), right after the accumulator registers have been handed to shared memory.
           const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);
           const int wrow0 = row0 + (warp & 3) * 32;                 // first global row of this warp's 32 rows
           const int nval = min(32, nrows - (warp & 3) * 32);        // rows of this warp that exist (may be <= 0)
@@ -510,48 +573,86 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
             for (int c4 = 0; c4 < 8; ++c4)
               sts128f(Tw + (lane * 36 + c4 * 4) * 4, make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
                                                                  __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3])));
+            float4 rs[8];
+            if (has_res) {
+#pragma unroll
+              for (int it8 = 0; it8 < 8; ++it8) {
+                const int rl = max(0, min(it8 * 4 + orow_l, nval - 1));         // clamped: always a row of this launch
+                rs[it8] = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol));
+              }
+            }
             __syncwarp();
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + ocol));
 #pragma unroll
             for (int it8 = 0; it8 < 8; ++it8) {
               const int rl = it8 * 4 + orow_l;
-              if (rl < nval) {
-                const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
-                float o[4] = {fmaf(t.x, scale, b4.x), fmaf(t.y, scale, b4.y), fmaf(t.z, scale, b4.z), fmaf(t.w, scale, b4.w)};
-                if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
-                const size_t goff = (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol;
-                if (has_res) {
-                  const float4 rs = __ldg(reinterpret_cast<const float4*>(a.res + goff));
-                  o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
-                }
-                *reinterpret_cast<float4*>(a.out + goff) = make_float4(o[0], o[1], o[2], o[3]);
-              }
+              const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
+              float o[4] = {fmaf(t.x, scale, b4.x), fmaf(t.y, scale, b4.y), fmaf(t.z, scale, b4.z), fmaf(t.w, scale, b4.w)};
+              if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
+              if (has_res) { o[0] += rs[it8].x; o[1] += rs[it8].y; o[2] += rs[it8].z; o[3] += rs[it8].w; }
+              if (rl < nval)
+                *reinterpret_cast<float4*>(a.out + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol) =
+                    make_float4(o[0], o[1], o[2], o[3]);
             }
             __syncwarp();
           }
         }
       } else {
         // ---- pass 1: m = SiLU(scale * D + b2), partial row dot with w_att / w6 over this thread's column half -----
-        float dot = 0.f;
+        // (packed fp32 pairs, one reciprocal shared by two values, two partial dots)
+        f32x2 dot2 = pk2(0.f, 0.f);
+        const f32x2 scale2 = pk2(scale, scale);
 #pragma unroll 1
         for (int cc = 0; cc < NCH; ++cc) {
           uint32_t v[32];
           tmem_ld32(taddr + cc * 32, v);
           tmem_ld_wait();
+#ifdef GEOLDM_SILU_QUAD
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const float4 b4 = lds128f(s_b2 + (cc * 32 + c8 * 8) * 4), b5 = lds128f(s_b2 + (cc * 32 + c8 * 8 + 4) * 4);
+            const float4 w4 = lds128f(s_wo + (cc * 32 + c8 * 8) * 4), w5 = lds128f(s_wo + (cc * 32 + c8 * 8 + 4) * 4);
+            f32x2 m0 = fma2(pk2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])), scale2, pk2(b4.x, b4.y));
+            f32x2 m1 = fma2(pk2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])), scale2, pk2(b4.z, b4.w));
+            f32x2 m2 = fma2(pk2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])), scale2, pk2(b5.x, b5.y));
+            f32x2 m3 = fma2(pk2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])), scale2, pk2(b5.z, b5.w));
+            silu_x8(m0, m1, m2, m3);
+            dot2 = fma2(pk2(w4.x, w4.y), m0, dot2);
+            dot2 = fma2(pk2(w4.z, w4.w), m1, dot2);
+            dot2 = fma2(pk2(w5.x, w5.y), m2, dot2);
+            dot2 = fma2(pk2(w5.z, w5.w), m3, dot2);
+            float f0, f1, f2, f3, f4, f5, f6, f7;
+            upk2(m0, f0, f1); upk2(m1, f2, f3); upk2(m2, f4, f5); upk2(m3, f6, f7);
+            v[c8 * 8 + 0] = __float_as_uint(f0); v[c8 * 8 + 1] = __float_as_uint(f1);
+            v[c8 * 8 + 2] = __float_as_uint(f2); v[c8 * 8 + 3] = __float_as_uint(f3);
+            v[c8 * 8 + 4] = __float_as_uint(f4); v[c8 * 8 + 5] = __float_as_uint(f5);
+            v[c8 * 8 + 6] = __float_as_uint(f6); v[c8 * 8 + 7] = __float_as_uint(f7);
+          }
+#else
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 b4 = lds128f(s_b2 + (cc * 32 + c4 * 4) * 4);
             const float4 w4 = lds128f(s_wo + (cc * 32 + c4 * 4) * 4);
-            const float m0 = silu(fmaf(__uint_as_float(v[c4 * 4 + 0]), scale, b4.x));
-            const float m1 = silu(fmaf(__uint_as_float(v[c4 * 4 + 1]), scale, b4.y));
-            const float m2 = silu(fmaf(__uint_as_float(v[c4 * 4 + 2]), scale, b4.z));
-            const float m3 = silu(fmaf(__uint_as_float(v[c4 * 4 + 3]), scale, b4.w));
-            dot = fmaf(w4.x, m0, dot); dot = fmaf(w4.y, m1, dot); dot = fmaf(w4.z, m2, dot); dot = fmaf(w4.w, m3, dot);
-            v[c4 * 4 + 0] = __float_as_uint(m0); v[c4 * 4 + 1] = __float_as_uint(m1);
-            v[c4 * 4 + 2] = __float_as_uint(m2); v[c4 * 4 + 3] = __float_as_uint(m3);
+            f32x2 m0 = fma2(pk2(__uint_as_float(v[c4 * 4 + 0]), __uint_as_float(v[c4 * 4 + 1])), scale2, pk2(b4.x, b4.y));
+            f32x2 m1 = fma2(pk2(__uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3])), scale2, pk2(b4.z, b4.w));
+            silu_x4(m0, m1);
+            dot2 = fma2(pk2(w4.x, w4.y), m0, dot2);
+            dot2 = fma2(pk2(w4.z, w4.w), m1, dot2);
+            float f0, f1, f2, f3;
+            upk2(m0, f0, f1);
+            upk2(m1, f2, f3);
+            v[c4 * 4 + 0] = __float_as_uint(f0); v[c4 * 4 + 1] = __float_as_uint(f1);
+            v[c4 * 4 + 2] = __float_as_uint(f2); v[c4 * 4 + 3] = __float_as_uint(f3);
           }
+#endif
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
+        }
+        float dot;
+        {
+          float d0, d1;
+          upk2(dot2, d0, d1);
+          dot = d0 + d1;
         }
         TC_PROF(const long long te3 = clock64(); te_p1 += te3 - te2;)
         float full_dot = dot;
@@ -567,7 +668,6 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         const bool head = valid && (lane == 0 || prev_i != my_i);
         const unsigned hm = __ballot_sync(0xffffffffu, head);
         const int nval = __popc(__ballot_sync(0xffffffffu, valid));
-        const int npiece = __popc(hm);
         if (MODE == MODE_EQUIV) {
           tc_fence_before();
           release_acc(region);
@@ -595,39 +695,52 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         } else {
           float g = a.attention ? sigmoidf_(full_dot + __ldg(a.b_out)) : 1.0f;
           if (!valid) g = 0.f;
+          const f32x2 g2 = pk2(g, g);
           TC_PROF(const long long te4 = clock64(); te_bar += te4 - te3;)
-          const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);     // this warp's [32][36] fp32 transposition tile
-          const uint32_t psw = sbase + S::OFF_PS + warp * (34 * 4);       // this warp's piece starts (+ end sentinel)
-          if (head) sts32i(psw + 4 * __popc(hm & ((1u << lane) - 1u)), lane);
-          if (lane == 0) sts32i(psw + 4 * npiece, nval);
-          __syncwarp();
+          // ---- pass 2: e = m * gate, summed over each receiver run of this warp's 32 rows -------------------------
+          // 32 x 32 chunks go through this warp's [32][36] fp32 transposition tile; lane (half, cp) then sums columns
+          // 2 cp, 2 cp + 1 over every second row of the run (64-bit loads), the two halves are folded with one shuffle
+          // and leave as one vector reduction per (run, column pair).  The summation order is fixed.
+          const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);
+          const int half = lane >> 4, cp = lane & 15;
+          uint32_t v[32];
+          tmem_ld32(taddr, v);
 #pragma unroll 1
           for (int cc = 0; cc < NCH; ++cc) {
-            uint32_t v[32];
-            tmem_ld32(taddr + cc * 32, v);
             tmem_ld_wait();
             if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-              float4 e4 = make_float4(__uint_as_float(v[c4 * 4]) * g, __uint_as_float(v[c4 * 4 + 1]) * g,
-                                      __uint_as_float(v[c4 * 4 + 2]) * g, __uint_as_float(v[c4 * 4 + 3]) * g);
-              sts128f(Tw + (lane * 36 + c4 * 4) * 4, e4);
+              float e0, e1, e2, e3;
+              upk2(mul2(pk2(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1])), g2), e0, e1);
+              upk2(mul2(pk2(__uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3])), g2), e2, e3);
+              sts128f(Tw + (lane * 36 + c4 * 4) * 4, make_float4(e0, e1, e2, e3));
             }
+            if (cc + 1 < NCH) tmem_ld32(taddr + (cc + 1) * 32, v);   // in flight while the rows of this chunk are summed
             __syncwarp();
-            for (int pc = 0; pc < npiece; ++pc) {
-              const int q0 = lds32i(psw + 4 * pc), q1 = lds32i(psw + 4 * pc + 4);
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-              uint32_t tp = Tw + (q0 * 36 + lane) * 4;
-              int q = q0;
-              for (; q + 4 <= q1; q += 4, tp += 4 * 36 * 4) {
-                s0 += lds32f(tp);
-                s1 += lds32f(tp + 36 * 4);
-                s2 += lds32f(tp + 72 * 4);
-                s3 += lds32f(tp + 108 * 4);
+            unsigned rest = hm;
+            while (rest) {
+              const int q0 = __ffs(rest) - 1;
+              rest &= rest - 1;
+              const int q1 = rest ? (__ffs(rest) - 1) : nval;
+              const int pi = __shfl_sync(0xffffffffu, my_i, q0);
+              f32x2 sA = pk2(0.f, 0.f), sB = sA;
+              // rows q0 + half, + 2, ... of the run, four 64-bit loads in flight (rows past the run read as zero)
+              for (int q = q0 + half; q < q1; q += 8) {
+                const uint32_t tp = Tw + (q * 36 + 2 * cp) * 4;
+                const f32x2 t0 = lds64(tp);
+                const f32x2 t1 = (q + 2 < q1) ? lds64(tp + 2 * 36 * 4) : pk2(0.f, 0.f);
+                const f32x2 t2 = (q + 4 < q1) ? lds64(tp + 4 * 36 * 4) : pk2(0.f, 0.f);
+                const f32x2 t3 = (q + 6 < q1) ? lds64(tp + 6 * 36 * 4) : pk2(0.f, 0.f);
+                sA = add2(sA, add2(t0, t2));
+                sB = add2(sB, add2(t1, t3));
               }
-              for (; q < q1; ++q, tp += 36 * 4) s0 += lds32f(tp);
-              const int pi = lds32i(s_i + 4 * ((warp & 3) * 32 + q0));
-              atomicAdd(a.out + (size_t)pi * H + hf * HC + cc * 32 + lane, (s0 + s1) + (s2 + s3));
+              sA = add2(sA, sB);
+              float s0, s1;
+              upk2(sA, s0, s1);
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              if (half == 0) red_add_v2(a.out + (size_t)pi * H + hf * HC + cc * 32 + 2 * cp, s0, s1);
             }
             __syncwarp();
           }
@@ -747,7 +860,7 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
 
 int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                      const float* pq, int pq_ld, const float* x, const float* x0, const float* r_edge,
-                     const float* d0_edge, float* out, cudaStream_t st) {
+                     const float* d0_edge, const float* u_edge, float* out, cudaStream_t st) {
   GEOLDM_REQUIRE(b.tile_m == TM, "edge_tc16: batch tile_m=%d, kernel needs %d", b.tile_m, TM);
   GEOLDM_REQUIRE(w.tc_pack != nullptr, "edge_tc16: tc_pack missing (weights not packed for the tensor-core path)");
   GEOLDM_REQUIRE(equiv || !cfg.attention || w.b_out != nullptr, "edge_tc16: attention needs b_out");
@@ -757,6 +870,7 @@ int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, co
   a.n_slabs = cfg.hidden_nf / BK;
   a.pq = pq; a.pq_ld = pq_ld; a.x = x; a.x0 = x0; a.edge_i = b.edge_i; a.edge_j = b.edge_j; a.w_rd = w.w_rd;
   a.r_edge = (r_edge && d0_edge) ? r_edge : nullptr; a.d0_edge = d0_edge;
+  a.u_edge = reinterpret_cast<const float4*>(u_edge);
   a.w_pack = reinterpret_cast<const uint8_t*>(w.tc_pack);
   a.b2 = w.b2; a.w_out = w.w_out; a.b_out = w.b_out; a.out = out;
   a.norm_constant = cfg.norm_constant; a.coords_range = cfg.coords_range;

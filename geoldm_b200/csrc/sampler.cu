@@ -384,17 +384,25 @@ int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, co
   return 0;
 }
 __global__ void edge_dist_kernel(int n_edge, const int* __restrict__ ei, const int* __restrict__ ej,
-                                 const float* __restrict__ x, float* __restrict__ out) {
+                                 const float* __restrict__ x, float* __restrict__ out, float4* __restrict__ u_out,
+                                 float norm_constant) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edge) return;
   const float* xi = x + 3 * (size_t)ei[e];
   const float* xj = x + 3 * (size_t)ej[e];
   const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-  out[e] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const float r = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  out[e] = r;
+  if (u_out) {      // same expression as edge_geom (common.cuh)
+    const float den = __fadd_rn(__fsqrt_rn(__fadd_rn(r, 1e-8f)), norm_constant);
+    u_out[e] = make_float4(__fdiv_rn(dx, den), __fdiv_rn(dy, den), __fdiv_rn(dz, den), 0.f);
+  }
 }
-int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, cudaStream_t st) {
+int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, float* u_out, float norm_constant,
+                     cudaStream_t st) {
   if (b.n_edge == 0) return 0;
-  edge_dist_kernel<<<(b.n_edge + 255) / 256, 256, 0, st>>>(b.n_edge, b.edge_i, b.edge_j, x, out);
+  edge_dist_kernel<<<(b.n_edge + 255) / 256, 256, 0, st>>>(b.n_edge, b.edge_i, b.edge_j, x, out,
+                                                           reinterpret_cast<float4*>(u_out), norm_constant);
   GEOLDM_CHECK_LAUNCH("edge_dist_kernel");
   return 0;
 }

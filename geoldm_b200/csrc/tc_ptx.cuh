@@ -237,6 +237,16 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// two consecutive fp32 as one packed pair (8-byte aligned)
+__device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+// out[0] += a, out[1] += b as ONE vector reduction (8-byte aligned global address; fire and forget)
+__device__ __forceinline__ void red_add_v2(float* out, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(out), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ float lds32f(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");

@@ -342,8 +342,12 @@ class EnLatentDiffusion(nn.Module):
         return out.view(kf * bs, n, -1)
 
     @torch.no_grad()
-    def sample_p_zs_given_zt(self, s, t, zt, node_mask, edge_mask, context, fix_noise=False, *, noise=None, seed=0):
-        """One ancestral step on padded tensors (compatibility path; s, t must be uniform over the batch)."""
+    def sample_p_zs_given_zt(self, s, t, zt, node_mask, edge_mask, context, fix_noise=False, *, noise=None, seed=0,
+                             draw=None):
+        """One ancestral step on padded tensors (compatibility path; s, t must be uniform over the batch).
+        Without injected ``noise`` the normals come from the Philox stream at draw index ``draw`` (default T - s, the
+        numbering of ``sample_latent_ragged``: 0 = z_T, 1 = step T-1, ...), so a reference-style loop over s draws
+        fresh noise at every step and reproduces ``sample`` with the same seed."""
         bs, n, D = zt.shape
         s_int = int(torch.round(s.reshape(-1)[0] * self.T).item())
         node_mask = node_mask.reshape(bs, n, 1)
@@ -358,9 +362,10 @@ class EnLatentDiffusion(nn.Module):
         mol_id = torch.zeros_like(batch.mol_id) if fix_noise else batch.mol_id
         cb = batch.c_batch(self.dynamics.egnn.tile_m())
         out_r = torch.empty_like(z_r)
+        draw_idx = torch.full((1,), self.T - s_int if draw is None else int(draw), dtype=torch.int32, device=dev)
         _lib.check(_lib.lib().geoldm_sampler_update(C.byref(cb), 0, _lib.ptr(table), _lib.ptr(step_idx), _lib.ptr(z_r),
                                                     _lib.ptr(eps), _lib.ptr(noise_r), 0, D, C.c_uint64(seed),
-                                                    _lib.ptr(mol_id), None, _lib.ptr(out_r), _stream(dev)),
+                                                    _lib.ptr(mol_id), _lib.ptr(draw_idx), _lib.ptr(out_r), _stream(dev)),
                    "geoldm_sampler_update")
         out = torch.zeros(bs * n, D, device=dev)
         out[src] = out_r

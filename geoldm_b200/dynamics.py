@@ -108,11 +108,15 @@ class _EgnnWrapper(nn.Module):
         return b
 
     def _wants_grad(self, xh, context):
-        """Autograd path (train.py) when a gradient can be asked for: grad mode on and either the module is in
-        train() mode or an input requires grad.  eval() + plain inputs -> the fused inference kernels."""
+        """Autograd path (train.py) whenever a gradient can be asked for, like the reference, which always builds the
+        graph: grad mode on and (train() mode, or an input requires grad, or any EGNN parameter requires grad — e.g.
+        eval()-mode NLL fine-tuning).  Sampling and evaluation run under torch.no_grad() (en_diffusion.py:762,1193) and
+        take the fused inference kernels."""
         if not torch.is_grad_enabled():
             return False
-        return self.training or xh.requires_grad or (context is not None and context.requires_grad)
+        if self.training or xh.requires_grad or (context is not None and context.requires_grad):
+            return True
+        return any(p.requires_grad for p in self.egnn.parameters())
 
     def _check_inputs(self, xh, node_mask):
         if not xh.is_cuda:

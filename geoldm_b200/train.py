@@ -65,9 +65,26 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+# Test seam, never set by the product: tests/ call `allow_cpu_graph_check(True)` to run THIS autograd graph (ragged
+# gathers, split first layer, segment sums, loss algebra, gloo all-reduce logic) on CPU tensors with library GEMMs
+# standing in for the CUDA kernels.  Without it a CPU tensor raises: there is no CPU path in the product.
+_CPU_GRAPH_CHECK = False
+
+
+def allow_cpu_graph_check(flag: bool = True):
+    global _CPU_GRAPH_CHECK
+    _CPU_GRAPH_CHECK = bool(flag)
+
+
+def _require_cuda(t):
+    if not t.is_cuda and not _CPU_GRAPH_CHECK:
+        raise _lib.GeoldmError("geoldm_b200 has no CPU path: the training graph needs CUDA tensors")
+
+
 def linear(x, weight, bias=None):
-    """nn.Linear forward/backward on our kernels when the shapes are GEMM-sized, library fallback for the tiny heads
+    """nn.Linear forward/backward on our kernels when the shapes are GEMM-sized; library op only for the tiny heads
     (embedding in/out, attention and coordinate heads: K or N < 16)."""
+    _require_cuda(x)
     K, N = weight.shape[1], weight.shape[0]
     if x.is_cuda and K % 16 == 0 and N % 16 == 0 and x.dtype == torch.float32:
         return _LinearFn.apply(x, weight, bias)
@@ -180,7 +197,8 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
         div = float(egnn.normalization_factor)
     fused = _fused_ok(h, H)
     d0, _ = _coord2diff(x, ei, ej, 1.0)
-    h = F.linear(h, egnn.embedding.weight, egnn.embedding.bias)
+    x0, dx = x, None        # the accumulated displacement is carried next to x: the dynamics' velocity x_final - x is
+    h = F.linear(h, egnn.embedding.weight, egnn.embedding.bias)   # then exact instead of a cancelling difference
     for b in range(egnn.n_layers):
         blk = getattr(egnn, f"e_block_{b}")
         r, u = _coord2diff(x, ei, ej, float(egnn.norm_constant))
@@ -208,9 +226,11 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
             m2 = F.silu(linear(a2, q.coord_mlp[2].weight, q.coord_mlp[2].bias))
             sc = F.linear(m2, q.coord_mlp[4].weight)
         trans = u * torch.tanh(sc) * egnn.coords_range if egnn.tanh else u * sc
-        x = x + torch.zeros(N, 3, device=x.device, dtype=x.dtype).index_add_(0, ei, trans) / div
+        step = torch.zeros(N, 3, device=x.device, dtype=x.dtype).index_add_(0, ei, trans) / div
+        dx = step if dx is None else dx + step
+        x = x0 + dx
     h = F.linear(h, egnn.embedding_out.weight, egnn.embedding_out.bias)
-    return h, x
+    return h, x, dx
 
 
 def _remove_mean_ragged(v, batch: RaggedBatch):
@@ -222,6 +242,7 @@ def _remove_mean_ragged(v, batch: RaggedBatch):
 
 def wrapper_forward_train(wrapper, t, xh, node_mask, edge_mask, context, is_dynamics: bool):
     """EGNN_dynamics_QM9._forward / EGNN_decoder_QM9._forward with autograd (padded in, padded out)."""
+    _require_cuda(xh)
     bs, n_nodes, dims = xh.shape
     batch = wrapper._masks.get(node_mask.view(bs, n_nodes, 1), edge_mask, wrapper.validate_masks)
     src = batch.node_src.long()
@@ -234,9 +255,9 @@ def wrapper_forward_train(wrapper, t, xh, node_mask, edge_mask, context, is_dyna
         h = torch.cat([h, t_mol.index_select(0, batch.node_mol.long()).unsqueeze(1)], dim=1)
     if context is not None:
         h = torch.cat([h, context.reshape(bs * n_nodes, -1).index_select(0, src)], dim=1)
-    h_f, x_f = egnn_forward_train(wrapper.egnn, h, x, batch)
+    h_f, x_f, dx = egnn_forward_train(wrapper.egnn, h, x, batch)
     if is_dynamics:
-        vel = x_f - x
+        vel = dx if dx is not None else x_f - x
         keep = wrapper.egnn.out_node_nf - wrapper.context_node_nf - int(wrapper.condition_time)
         h_f = h_f[:, :keep]
     else:

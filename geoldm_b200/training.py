@@ -71,17 +71,19 @@ def get_optim(args, generative_model):
 
 
 def gradient_buckets(model) -> List[List[torch.nn.Parameter]]:
-    """Parameters that can receive a gradient, grouped per sub-network in reverse registration order (the order in
-    which backward produces them): decoder first, then the denoiser.  The encoder is never in a bucket: its output is
-    detached (en_diffusion.py:1155)."""
-    groups = {"vae.decoder": [], "dynamics": []}
+    """EVERY parameter that can receive a gradient, grouped per sub-network, sub-networks and their parameters in
+    reverse registration order (the order in which backward produces them): for the latent model the decoder first,
+    then the denoiser (its encoder is frozen inside `forward`: en_diffusion.py:1155, and carries no gradient unless
+    the first stage is trainable); for a first-stage EnHierarchicalVAE the decoder, then the encoder.  A parameter with
+    requires_grad that is in no bucket would make the ranks diverge silently, so every one lands in a bucket."""
+    groups: dict = {}
     for name, p in model.named_parameters():
         if not p.requires_grad:
             continue
-        for key in groups:
-            if name.startswith(key):
-                groups[key].append(p)
-    return [list(reversed(g)) for g in (groups["vae.decoder"], groups["dynamics"]) if g]
+        parts = name.split(".")
+        key = ".".join(parts[:2]) if parts[0] == "vae" and len(parts) > 2 else parts[0]
+        groups.setdefault(key, []).append(p)
+    return [list(reversed(g)) for g in reversed(list(groups.values())) if g]
 
 
 def allreduce_gradients(buckets: Iterable[List[torch.nn.Parameter]], group=None) -> int:

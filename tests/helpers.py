@@ -80,4 +80,13 @@ def assert_parity(tag, out, ref32, ref64, tol=1e-5):
     print(f"[parity] {tag}: ours-vs-fp64 x {ex64:.2e} h {eh64:.2e} | ours-vs-ref32 x {ex32:.2e} h {eh32:.2e} | "
           f"ref32-vs-fp64 (reference noise floor) x {fx:.2e} h {fh:.2e}")
     assert ex64 < tol and eh64 < tol, (tag, "vs fp64", ex64, eh64)
-    assert ex32 < tol + fx and eh32 < tol + fh, (tag, "vs ref32", ex32, eh32, fx, fh)
+    # north_star's gate as written — within `tol` of the reference's own fp32 output — is asserted as such wherever it
+    # is well-posed, i.e. where the reference's own rounding noise (ref32 vs fp64) is small against tol.  Measured on
+    # B200: that holds for every h part (<= 2.3e-6) and for most x parts; the x part of the reference itself is 1.4e-5
+    # (QM9 t=0.5), 1.5e-5 ('mean'), 2.9e-5 (nf=32 'mean') and 5.9e-3 (tanh off, normalization 100) away from the exact
+    # result in a few fixtures, where only the floor-adjusted form can be asked of anyone.
+    for part, e32, floor in (("x", ex32, fx), ("h", eh32, fh)):
+        if floor < 0.3 * tol:
+            assert e32 < tol, (tag, part, "vs ref32 (plain gate)", e32, "reference floor", floor)
+        else:
+            assert e32 < tol + floor, (tag, part, "vs ref32 (floor-adjusted gate)", e32, "reference floor", floor)

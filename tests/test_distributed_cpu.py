@@ -57,6 +57,8 @@ def test_sharded_sampling_matches_single_rank(tmp_path):
 def _patch_cpu_autograd():
     """Route the wrappers through train.py's library-op graph so the host logic can run on CPU in this test."""
     from geoldm_b200 import dynamics
+    from geoldm_b200 import train as _train
+    _train.allow_cpu_graph_check(True)       # test seam: library GEMMs stand in for the CUDA kernels (no GPU here)
     dynamics._EgnnWrapper._check_inputs = lambda self, xh, nm: None
     dynamics._EgnnWrapper._wants_grad = lambda self, xh, ctx: True
 
@@ -108,6 +110,8 @@ def test_two_rank_training_step_matches_single_rank(tmp_path, monkeypatch):
     port = 29950 + os.getpid() % 40
     mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     from geoldm_b200 import dynamics
+    from geoldm_b200 import train as _train
+    monkeypatch.setattr(_train, "_CPU_GRAPH_CHECK", True)
     monkeypatch.setattr(dynamics._EgnnWrapper, "_check_inputs", lambda self, xh, nm: None)
     monkeypatch.setattr(dynamics._EgnnWrapper, "_wants_grad", lambda self, xh, ctx: True)
     model, nodes_dist, data, args = _train_setup()

@@ -138,3 +138,22 @@ def test_model_deepcopy_for_ema():
     a, b = model.state_dict(), clone.state_dict()
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
     assert all(p.data_ptr() != q.data_ptr() for p, q in zip(model.parameters(), clone.parameters()) if p.numel())
+
+
+def test_product_distribution_nodes_matches_reference_draws():
+    """a17: the PRODUCT class geoldm_b200.models.DistributionNodes (not the oracle's function) reproduces the reference's
+    draws for torch.manual_seed(0) (fixture written by oracle/make_golden.py from qm9/models.py:178-215) and its
+    log-probabilities."""
+    import numpy as np
+    from geoldm_b200.histograms import QM9_WITH_H_N_NODES
+    from geoldm_b200.models import DistributionNodes
+    from tests.helpers import GOLDEN
+    want = np.load(os.path.join(GOLDEN, "nodes_dist_qm9_seed0.npz"))["draws"]
+    torch.manual_seed(0)
+    nd = DistributionNodes(QM9_WITH_H_N_NODES)
+    got = nd.sample(64)
+    assert np.array_equal(got.numpy(), want)
+    p = np.array(list(QM9_WITH_H_N_NODES.values()), dtype=np.float64)
+    lp = nd.log_prob(torch.tensor([29, 9, 18]))
+    idx = [list(QM9_WITH_H_N_NODES.keys()).index(k) for k in (29, 9, 18)]
+    assert np.allclose(lp.numpy(), np.log(p[idx] / p.sum()), rtol=1e-6)

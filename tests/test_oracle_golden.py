@@ -121,3 +121,44 @@ def test_step_coefficients_match_tensor_path():
         a_ts, c_eps, c_noise = O.step_coefficients(gamma, 1000, s)
         assert torch.isfinite(a_ts) and torch.isfinite(c_eps) and torch.isfinite(c_noise)
         assert 0 < float(a_ts) <= 1.0
+
+
+@pytest.mark.parametrize("name", ["v64_default", "v64_noatt", "v64_notanh", "v64_S2_noatt_notanh", "v64_mean",
+                                  "v64_cond_latent2"])
+def test_flag_variants_nf64(name):
+    """Round-2 fixtures (oracle/make_golden_r2.py): every constructor flag at hidden_nf = 64, incl. 2- and 1-atom molecules."""
+    cfg, sd, a, _ = load_golden(name)
+    nm, em = O.build_masks(a["nodes"].tolist(), 29)
+    ctx = a.get("context")
+    with torch.no_grad():
+        out = O.dynamics_forward(sd, cfg, a["t_vec"], a["z"], nm, em, ctx)
+        dx, dh = O.decoder_forward(sd, cfg, a["z"], nm, em, ctx)
+    ex, eh = part_errors(out, a["out"])
+    assert ex < TOL and eh < TOL, (ex, eh)
+    assert O.err_metric(dx, a["dec_x"]) < TOL and O.err_metric(dh, a["dec_h"]) < TOL
+
+
+def test_full_size_trajectory_fixture_teacher_forced():
+    """qm9_full_tamed_T1000 (complete 1000-step reference run at nf=256, 9 layers): the oracle reproduces eps_hat and z_s
+    of stored steps early, in the middle and at the end of the trajectory, and p(x, h | z_0)."""
+    cfg, sd, a, _ = load_golden("qm9_full_tamed_T1000")
+    nodes = a["nodes"].tolist()
+    bs, T, D = len(nodes), cfg.diffusion_steps, 3 + cfg.latent_nf
+    nm, em = O.build_masks(nodes, 29)
+    raw = torch.randn(T + 2, bs, 29, D, generator=torch.Generator().manual_seed(int(a["noise_seed"][0])))
+    steps = a["steps"].tolist()
+    with torch.no_grad():
+        for k in (0, len(steps) // 2, len(steps) - 1):
+            s = steps[k]
+            s_arr = torch.full((bs, 1), float(s)) / T
+            t_arr = torch.full((bs, 1), float(s + 1)) / T
+            src = O.NoiseSource(raw.double()); src.k = T - s
+            zs, eps = O.sample_p_zs_given_zt(sd, cfg, s_arr, t_arr, a["zt"][k], nm, em, None, src, True)
+            ex, eh = part_errors(eps, a["eps"][k])
+            assert ex < TOL and eh < TOL, ("eps", s, ex, eh)
+            ex, eh = part_errors(zs, a["zs"][k])
+            assert ex < TOL and eh < TOL, ("zs", s, ex, eh)
+        src = O.NoiseSource(raw.double()); src.k = T + 1
+        x, h = O.sample_p_xh_given_z0(sd, cfg, a["z0"], nm, em, None, src)
+        ex, eh = part_errors(torch.cat([x, h], 2), a["xh0"])
+        assert ex < TOL and eh < TOL, ("xh0", ex, eh)

@@ -44,6 +44,8 @@ def _force_autograd_everywhere(model, monkeypatch):
     """CPU-only check of losses.py + the autograd graph: route every wrapper through train.py's library-op graph.
     (The product refuses CPU tensors; this patches the test's own model instance.)"""
     from geoldm_b200 import dynamics
+    from geoldm_b200 import train as _train
+    monkeypatch.setattr(_train, "_CPU_GRAPH_CHECK", True)        # test seam, see train.allow_cpu_graph_check
     monkeypatch.setattr(dynamics._EgnnWrapper, "_check_inputs", lambda self, xh, nm: None)
     monkeypatch.setattr(dynamics._EgnnWrapper, "_wants_grad", lambda self, xh, ctx: True)
 
