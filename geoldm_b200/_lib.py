@@ -63,6 +63,11 @@ _SIGS = {
     "geoldm_sampler_advance": (C.c_int, [fp, C.c_int, fp, C.c_int, fp]),
     "geoldm_edge_gcl": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EdgeMlp), C.POINTER(Batch), fp, fp, fp, fp, fp]),
     "geoldm_edge_equiv": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EdgeMlp), C.POINTER(Batch), fp, fp, fp, fp, fp]),
+    "geoldm_edge_dist": (C.c_int, [C.POINTER(Batch), fp, fp, fp, C.c_float, fp]),
+    "geoldm_edge_gcl_pre": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EdgeMlp), C.POINTER(Batch), fp, C.c_int, fp, fp,
+                                      fp, fp]),
+    "geoldm_edge_equiv_pre": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EdgeMlp), C.POINTER(Batch), fp, C.c_int, fp,
+                                        fp, fp, fp, fp]),
     "geoldm_linear": (C.c_int, [fp, C.c_int, fp, C.c_int, C.c_float, fp, fp, fp, C.c_int, fp, C.c_int, C.c_int,
                                 C.c_int, fp]),
     "geoldm_tc_pack_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -104,7 +109,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.geoldm_abi_version() != 2:
+        if handle.geoldm_abi_version() != 3:
             raise GeoldmError("ABI version mismatch between _lib.py and libgeoldm_b200.so")
         _lib = handle
     return _lib

@@ -167,6 +167,25 @@ int geoldm_edge_equiv(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, c
   if (int rc = check_cfg(cfg)) return rc;
   return edge_dispatch(*cfg, *w, *b, true, pq, 2 * cfg->hidden_nf, x, x0, xagg, (cudaStream_t)stream);
 }
+int geoldm_edge_dist(const geoldm_batch* b, const float* x, float* r_out, float* u_out, float norm_constant,
+                     void* stream) {
+  return launch_edge_dist(*b, x, r_out, u_out, norm_constant, (cudaStream_t)stream);
+}
+int geoldm_edge_gcl_pre(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b, const float* pq,
+                        int pq_ld, const float* r_edge, const float* d0_edge, float* agg, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  GEOLDM_REQUIRE(cfg->mma_mode == GEOLDM_MMA_3XF16 && r_edge && d0_edge, "edge_gcl_pre: mma_mode 3xf16 with r_edge/d0_edge");
+  return edge_dispatch(*cfg, *w, *b, false, pq, pq_ld, nullptr, nullptr, agg, (cudaStream_t)stream, r_edge, d0_edge);
+}
+int geoldm_edge_equiv_pre(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b,
+                          const float* pq, int pq_ld, const float* r_edge, const float* d0_edge, const float* u_edge,
+                          float* xagg, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  GEOLDM_REQUIRE(cfg->mma_mode == GEOLDM_MMA_3XF16 && r_edge && d0_edge && u_edge,
+                 "edge_equiv_pre: mma_mode 3xf16 with r_edge/d0_edge/u_edge");
+  return edge_dispatch(*cfg, *w, *b, true, pq, pq_ld, nullptr, nullptr, xagg, (cudaStream_t)stream, r_edge, d0_edge,
+                       u_edge);
+}
 int geoldm_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt, const float* bias,
                   const float* res, int epi, float* out, int m, int n, int mma_mode, void* stream) {
   (void)mma_mode;

@@ -573,27 +573,46 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
             for (int c4 = 0; c4 < 8; ++c4)
               sts128f(Tw + (lane * 36 + c4 * 4) * 4, make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
                                                                  __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3])));
-            float4 rs[8];
             if (has_res) {
+              __syncwarp();
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + ocol));
+#ifndef GEOLDM_RES_BATCH
+#define GEOLDM_RES_BATCH 8
+#endif
+#pragma unroll
+              for (int hb = 0; hb < 8 / GEOLDM_RES_BATCH; ++hb) {          // residual rows in batches of coalesced loads
+                float4 rs[GEOLDM_RES_BATCH];
+#pragma unroll
+                for (int k = 0; k < GEOLDM_RES_BATCH; ++k) {
+                  const int rl = max(0, min((hb * GEOLDM_RES_BATCH + k) * 4 + orow_l, nval - 1));   // clamped: in bounds
+                  rs[k] = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol));
+                }
+#pragma unroll
+                for (int k = 0; k < GEOLDM_RES_BATCH; ++k) {
+                  const int rl = (hb * GEOLDM_RES_BATCH + k) * 4 + orow_l;
+                  const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
+                  if (rl < nval)
+                    *reinterpret_cast<float4*>(a.out + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol) =
+                        make_float4(fmaf(t.x, scale, b4.x) + rs[k].x, fmaf(t.y, scale, b4.y) + rs[k].y,
+                                    fmaf(t.z, scale, b4.z) + rs[k].z, fmaf(t.w, scale, b4.w) + rs[k].w);
+                }
+              }
+            } else {
+              __syncwarp();
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + ocol));
 #pragma unroll
               for (int it8 = 0; it8 < 8; ++it8) {
-                const int rl = max(0, min(it8 * 4 + orow_l, nval - 1));         // clamped: always a row of this launch
-                rs[it8] = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol));
+                const int rl = it8 * 4 + orow_l;
+                if (rl < nval) {
+                  const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
+                  float o[4] = {fmaf(t.x, scale, b4.x), fmaf(t.y, scale, b4.y), fmaf(t.z, scale, b4.z), fmaf(t.w, scale, b4.w)};
+                  if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
+                  *reinterpret_cast<float4*>(a.out + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol) =
+                      make_float4(o[0], o[1], o[2], o[3]);
+                }
               }
-            }
-            __syncwarp();
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + ocol));
-#pragma unroll
-            for (int it8 = 0; it8 < 8; ++it8) {
-              const int rl = it8 * 4 + orow_l;
-              const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
-              float o[4] = {fmaf(t.x, scale, b4.x), fmaf(t.y, scale, b4.y), fmaf(t.z, scale, b4.z), fmaf(t.w, scale, b4.w)};
-              if (MODE == MODE_DENSE && a.epi == 1) { o[0] = silu(o[0]); o[1] = silu(o[1]); o[2] = silu(o[2]); o[3] = silu(o[3]); }
-              if (has_res) { o[0] += rs[it8].x; o[1] += rs[it8].y; o[2] += rs[it8].z; o[3] += rs[it8].w; }
-              if (rl < nval)
-                *reinterpret_cast<float4*>(a.out + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol) =
-                    make_float4(o[0], o[1], o[2], o[3]);
             }
             __syncwarp();
           }

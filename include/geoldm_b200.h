@@ -28,7 +28,7 @@ extern "C" {
 
 #define GEOLDM_MAX_LAYERS 16
 #define GEOLDM_MAX_SUBLAYERS 4
-#define GEOLDM_ABI_VERSION 2
+#define GEOLDM_ABI_VERSION 3
 
 /* arithmetic mode of the 256x256 edge/node contractions */
 enum {
@@ -161,6 +161,19 @@ int geoldm_sampler_advance(int* step_idx_dev, int d_step, int* draw_idx_dev, int
 /* a1+a3 edge part: agg[i] += sum_j e_ij (raw sum; caller zeroes agg and divides by agg_div) */
 int geoldm_edge_gcl(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b,
                     const float* pq, const float* x, const float* x0, float* agg, void* stream);
+/* a1 (coord2diff, egnn/egnn_new.py:249-255) for every packed edge row e = (i, j): r_out[e] = |x_i - x_j|^2 and, when
+ * u_out != NULL, u_out[4e .. 4e+2] = (x_i - x_j) / (sqrt(r + 1e-8) + norm_constant), u_out[4e+3] = 0.  geoldm_egnn_forward
+ * runs this once per block (mma_mode 3xf16) and feeds the results to the fused edge kernels below. */
+int geoldm_edge_dist(const geoldm_batch* b, const float* x, float* r_out, float* u_out, float norm_constant,
+                     void* stream);
+/* the fused edge kernels exactly as geoldm_egnn_forward launches them in mma_mode 3xf16: per-edge squared distances of
+ * the current (r_edge) and the EGNN-entry (d0_edge) coordinates and, for the coordinate update, the normalised differences
+ * u_edge ([E][4]) are read instead of being recomputed from x; pq is [N][pq_ld] (P in columns [0,H), Q in [H,2H)). */
+int geoldm_edge_gcl_pre(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b, const float* pq,
+                        int pq_ld, const float* r_edge, const float* d0_edge, float* agg, void* stream);
+int geoldm_edge_equiv_pre(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b,
+                          const float* pq, int pq_ld, const float* r_edge, const float* d0_edge, const float* u_edge,
+                          float* xagg, void* stream);
 /* a1+a4: xagg[i] += sum_j u_ij * tanh(s_ij) * coords_range (raw sum) */
 int geoldm_edge_equiv(const geoldm_egnn_config* cfg, const geoldm_edge_mlp* w, const geoldm_batch* b,
                       const float* pq, const float* x, const float* x0, float* xagg, void* stream);

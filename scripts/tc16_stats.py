@@ -25,15 +25,24 @@ pq = torch.randn(batch.n_node, 2 * H, device=dev)
 xx = torch.randn(batch.n_node, 3, device=dev)
 import os as _os
 out = (C.c_ulonglong * 16)()
-for name, fn, em, o in (("GCL", L.geoldm_edge_gcl, w.block[0].gcl[0].edge, torch.zeros(batch.n_node, H, device=dev)),
-                        ("EQUIV", L.geoldm_edge_equiv, w.block[0].equiv, torch.zeros(batch.n_node, 3, device=dev))):
+# same inputs as geoldm_egnn_forward feeds the kernels: per-edge squared distances and normalised differences
+r_e = torch.empty(batch.n_edge, device=dev)
+u_e = torch.empty(batch.n_edge, 4, device=dev)
+_lib.check(L.geoldm_edge_dist(C.byref(cb), _lib.ptr(xx), _lib.ptr(r_e), _lib.ptr(u_e), 1.0, None), "edge_dist")
+o_gcl, o_eq = torch.zeros(batch.n_node, H, device=dev), torch.zeros(batch.n_node, 3, device=dev)
+gcl_e, eq_e = w.block[0].gcl[0].edge, w.block[0].equiv
+runs = (("GCL", lambda: L.geoldm_edge_gcl_pre(C.byref(ccfg), C.byref(gcl_e), C.byref(cb), _lib.ptr(pq), 2 * H, _lib.ptr(r_e),
+                                               _lib.ptr(r_e), _lib.ptr(o_gcl), None)),
+        ("EQUIV", lambda: L.geoldm_edge_equiv_pre(C.byref(ccfg), C.byref(eq_e), C.byref(cb), _lib.ptr(pq), 2 * H, _lib.ptr(r_e),
+                                                   _lib.ptr(r_e), _lib.ptr(u_e), _lib.ptr(o_eq), None)))
+for name, fn in runs:
     for _ in range(3):
-        _lib.check(fn(C.byref(ccfg), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xx), _lib.ptr(xx), _lib.ptr(o), None), name)
+        _lib.check(fn(), name)
     L.geoldm_tc16_read_stats(out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        _lib.check(fn(C.byref(ccfg), C.byref(em), C.byref(cb), _lib.ptr(pq), _lib.ptr(xx), _lib.ptr(xx), _lib.ptr(o), None), name)
+        _lib.check(fn(), name)
     e1.record()
     L.geoldm_tc16_read_stats(out)
     print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us per launch (events, 5 back-to-back launches)")
