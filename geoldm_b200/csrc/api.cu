@@ -101,6 +101,16 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
   const float* d0_edge = pre_dist ? ws.d0_edge : nullptr;
   const float* u_edge = pre_dist ? ws.u_edge : nullptr;
   if (pre_dist && (rc = launch_edge_dist(*b, x_in, ws.d0_edge, ws.u_edge, cfg->norm_constant, st))) return rc;
+  // segment-sum targets: the fp16-split path clears them ONCE here; afterwards their consumers (the residual epilogue
+  // of node_mlp.2 for agg, the coordinate update for xagg) hand them back zeroed - 2 memset nodes per forward instead
+  // of 2 per block.  The other modes clear them before every edge kernel.
+  const bool self_clean = cfg->mma_mode == GEOLDM_MMA_3XF16;
+  if (self_clean) {
+    cudaError_t e1 = cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
+    cudaError_t e2 = cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
+    GEOLDM_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "egnn_forward: memset failed: %s",
+                   cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
   for (int l = 0; l < cfg->n_layers; ++l) {
     const geoldm_block& blk = w->block[l];
     if (pre_dist) {
@@ -118,11 +128,15 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
       } else {
         if ((rc = launch_linear(h, H, nullptr, 0, 1.f, g.edge.pq_wt, g.edge.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
       }
-      cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
+      if (!self_clean) {
+        cudaError_t e = cudaMemsetAsync(ws.agg, 0, (size_t)N * H * sizeof(float), st);
+        GEOLDM_REQUIRE(e == cudaSuccess, "egnn_forward: memset failed: %s", cudaGetErrorString(e));
+      }
       if ((rc = edge_dispatch(*cfg, g.edge, *b, false, pq, pq_ld, x_cur, x_in, ws.agg, st, r_edge, d0_edge))) return rc;
       if (tcore) {
         if ((rc = launch_linear_tc(H, terms, h, H, ws.agg, H, cfg->agg_div, g.tc_pack_node1, 1, g.node_b1, nullptr, 1, ws.t1, N, st))) return rc;
-        if ((rc = launch_linear_tc(H, terms, ws.t1, H, nullptr, 0, 1.f, g.tc_pack_node2, 1, g.node_b2, h, 2, h2, N, st))) return rc;
+        if ((rc = launch_linear_tc(H, terms, ws.t1, H, nullptr, 0, 1.f, g.tc_pack_node2, 1, g.node_b2, h, 2, h2, N, st,
+                                   self_clean ? ws.agg : nullptr))) return rc;
       } else {
         if ((rc = launch_linear(h, H, ws.agg, H, cfg->agg_div, g.node_w1t, g.node_b1, nullptr, 1, ws.t1, N, H, st))) return rc;
         if ((rc = launch_linear(ws.t1, H, nullptr, 0, 1.f, g.node_w2t, g.node_b2, h, 2, h2, N, H, st))) return rc;
@@ -142,12 +156,16 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
     } else {
       if ((rc = launch_linear(h, H, nullptr, 0, 1.f, e.pq_wt, e.pq_b, nullptr, 0, ws.pq, N, 2 * H, st))) return rc;
     }
-    cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
+    if (!self_clean) {
+      cudaError_t em = cudaMemsetAsync(ws.xagg, 0, (size_t)3 * N * sizeof(float), st);
+      GEOLDM_REQUIRE(em == cudaSuccess, "egnn_forward: memset failed: %s", cudaGetErrorString(em));
+    }
     if ((rc = edge_dispatch(*cfg, e, *b, true, ws.pq, pq_ld, x_cur, x_in, ws.xagg, st, r_edge, d0_edge, u_edge))) return rc;
     const bool last = (l + 1 == cfg->n_layers);
     float* x_next = last ? x_out : x_bufs[xi];
     float* dx_next = (last && dx_out) ? dx_out : ws.dx;   // dx is updated in place (elementwise)
-    if ((rc = launch_coord_update(3 * N, x_in, l == 0 ? nullptr : ws.dx, ws.xagg, cfg->agg_div, dx_next, x_next, st)))
+    if ((rc = launch_coord_update(3 * N, x_in, l == 0 ? nullptr : ws.dx, ws.xagg, cfg->agg_div, dx_next, x_next, st,
+                                  self_clean)))
       return rc;
     x_cur = x_next;
     xi ^= 1;

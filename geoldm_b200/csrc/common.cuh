@@ -168,7 +168,7 @@ int launch_linear(const float* a1, int k1, const float* a2, int k2, float a2_div
 
 int launch_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
                      const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out, int m,
-                     cudaStream_t st);
+                     cudaStream_t st, float* zero_buf = nullptr);
 int launch_tc_selftest(int H, int terms, const float* pq, const int* edge_i, const int* tile_row, int n_tile,
                        int n_rows, const void* w_pack, float* out, cudaStream_t st);
 // fp16-split variants (edge_tc16.cu), selected by terms == 16 / GEOLDM_MMA_3XF16
@@ -180,14 +180,15 @@ int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, co
 int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, float* u_out, float norm_constant,
                      cudaStream_t st);
 int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
-                       int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st);
+                       int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st,
+                       float* zero_buf = nullptr);   // zero_buf: [m][n_blocks H] buffer cleared by the residual epilogue
 int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,
                          const void* w_pack, float* out, cudaStream_t st);
 int launch_embed(int n_node, int H, int F, const float* h_in, const float* w, const float* b, float* h,
                  cudaStream_t st);
 int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, const float* b, float* out,
                    cudaStream_t st);
-int launch_coord_update(int n3, const float* x0, const float* dx, const float* xagg, float div, float* dx_next,
-                        float* x_next, cudaStream_t st);
+int launch_coord_update(int n3, const float* x0, const float* dx, float* xagg, float div, float* dx_next,
+                        float* x_next, cudaStream_t st, bool zero_xagg = false);
 
 }  // namespace geoldm

@@ -788,8 +788,9 @@ int launch_edge_tc(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, cons
 // out[M][ldo] (column block nb: columns [nb*H, nb*H+H)) = epi(A * W_nb^T + bias) (+res);  A = [a1 | a2/a2_div]
 int launch_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
                      const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out, int m,
-                     cudaStream_t st) {
-  if (terms == 16) return launch_linear_tc16(H, a1, k1, a2, k2, a2_div, w_pack, n_blocks, bias, res, epi, out, m, st);
+                     cudaStream_t st, float* zero_buf) {
+  if (terms == 16) return launch_linear_tc16(H, a1, k1, a2, k2, a2_div, w_pack, n_blocks, bias, res, epi, out, m, st, zero_buf);
+  GEOLDM_REQUIRE(zero_buf == nullptr, "linear_tc: zero_buf is implemented by the fp16-split kernels only");
   GEOLDM_REQUIRE(k1 % BK == 0 && k2 % BK == 0 && k1 + k2 > 0, "linear_tc: k1=%d k2=%d must be multiples of %d", k1, k2, BK);
   GEOLDM_REQUIRE(w_pack != nullptr, "linear_tc: w_pack missing");
   TcArgs a{};

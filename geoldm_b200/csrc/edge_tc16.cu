@@ -35,7 +35,9 @@ using namespace tc;
 
 constexpr int TM = 128;          // rows per tile (TMEM lanes)
 constexpr int BK = 64;           // k-slab: 64 fp16 = 128 bytes per row = one swizzle row
-constexpr int NWS = 3;           // W pipeline stages
+#ifndef GEOLDM_EQUIV_SPS
+#define GEOLDM_EQUIV_SPS 1
+#endif
 // Warp roles per mode.  The A generator is latency bound (two dependent global-load phases per k-slab and thread), so
 // EQUIV, DENSE and RAW run 16 producer warps (2 rows x 8 columns per thread and slab, one load phase) next to the 8
 // epilogue warps (832 threads, 72 registers); GCL keeps 8 + 8 (576 threads, 96 registers): its tail (second SiLU, gate,
@@ -73,6 +75,7 @@ struct Args {
   const uint8_t* w_pack;    // header + [block][slab][N-half][hi image | lo image]
   const float* b2; const float* w_out; const float* b_out; const float* res;
   float* out; int ldo; int epi;
+  float* zero_buf;          // DENSE residual epilogue: same layout as out, cleared on the way (the consumed agg buffer)
   float norm_constant, coords_range;
   int attention, use_tanh;
   float rz_scale;           // 1 + RZ_BIAS_PER_MMA * (#MMAs accumulated per output)
@@ -80,14 +83,19 @@ struct Args {
 
 template <int H, int MODE>
 struct Smem {
-  static constexpr int NAS = (MODE == 1) ? 3 : 2;             // A pipeline stages (the others spend 36 KB on transposition tiles)
+  // A pipeline: NAS stages of SPS k-slabs each (one wait / proxy fence / arrive per STAGE), W pipeline: NWS k-slab stages.
+  // EQUIV has no transposition tiles and can spend that shared memory on two-slab A stages (half the hand-offs per tile).
+  static constexpr int SPS = (MODE == 1 && (H / 64) % 2 == 0) ? GEOLDM_EQUIV_SPS : 1;
+  static constexpr int NAS = (MODE == 1) ? (SPS == 2 ? 2 : 3) : 2;
+  static constexpr int NWS = (SPS == 2) ? 2 : 3;
   // warp-private [32 rows][36 floats] transposition tiles: GCL 8 warps (segment sum), DENSE / RAW 4 warps (coalesced
   // output rows); EQUIV needs none
   static constexpr uint32_t T_BYTES = (MODE == 1) ? 0u : 8u * 32 * 36 * 4;
   static constexpr uint32_t NH = H / 2;
   static constexpr uint32_t W_IMG = NH * 128u;
   static constexpr uint32_t W_STAGE = 2u * W_IMG;
-  static constexpr uint32_t A_STAGE = 2u * TM * 128u;
+  static constexpr uint32_t A_SLAB = 2u * TM * 128u;          // hi | lo images of one 64-column k-slab
+  static constexpr uint32_t A_STAGE = SPS * A_SLAB;
   static constexpr uint32_t OFF_W = 0;
   static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
   static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
   using R = Roles<MODE>;
   constexpr int NTHREADS = R::NTHREADS, EPI_T = R::EPI_T, WARP_LOAD = R::WARP_LOAD, WARP_MMA = R::WARP_MMA;
   constexpr int ROWS_PT = R::ROWS_PT, NHALF = R::NHALF;
-  constexpr int NAS = S::NAS;
+  constexpr int NAS = S::NAS, NWS = S::NWS, SPS = S::SPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -260,16 +268,16 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + region * 256;
         for (int s = 0; s < a.n_slabs; ++s, ++ait, ++wit) {
-          const int ast = ait % NAS, wst = wit % NWS;
+          const int ast = (ait / SPS) % NAS, sub = ait % SPS, wst = wit % NWS;
           TC_PROF(t0 = clock64();)
-          mbar_wait_cluster(&a_full[ast], (ait / NAS) & 1);
+          if (sub == 0) mbar_wait_cluster(&a_full[ast], ((ait / SPS) / NAS) & 1);
           TC_PROF(long long t1 = clock64();)
           mbar_wait(&w_full[wst], (wit / NWS) & 1);
           mbar_wait_cluster(&w_peer[wst], (wit / NWS) & 1);
           TC_PROF(t_a += t1 - t0; t_w += clock64() - t1;)
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_hi = smem_u32(smem + S::OFF_A + ast * S::A_STAGE);
+            const uint32_t a_hi = smem_u32(smem + S::OFF_A + ast * S::A_STAGE + sub * S::A_SLAB);
             const uint32_t a_lo = a_hi + TM * 128;
             const uint32_t w_hi = smem_u32(smem + S::OFF_W + wst * S::W_STAGE);
             const uint32_t w_lo = w_hi + S::W_IMG;
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               mma_f16_pair(d_tmem, da_hi, dw_hi, idesc, 1);
             }
             mma_commit_pair(&w_empty[wst], cmask);
-            mma_commit_pair(&a_empty[ast], cmask);
+            if (sub == SPS - 1) mma_commit_pair(&a_empty[ast], cmask);
             if (s == a.n_slabs - 1) mma_commit_pair(&acc_full[region], cmask);
           }
           __syncwarp();
@@ -375,11 +383,11 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       const int n_slabs_p = (MODE == MODE_DENSE) ? a.n_slabs : KS_STATIC;
 #pragma unroll(MODE == MODE_DENSE ? 1 : KS_STATIC)
       for (int s = 0; s < n_slabs_p; ++s, ++it) {
-        const int st = it % NAS;
+        const int st = (it / SPS) % NAS, sub = it % SPS;
         const int k0 = s * BK;
         TC_PROF(const long long tp0 = clock64(); long long tp1 = tp0;)
-        bool waited = false;
-        const uint32_t a_hi = sbase + S::OFF_A + st * S::A_STAGE;
+        bool waited = sub != 0;                      // the stage was acquired with its first slab
+        const uint32_t a_hi = sbase + S::OFF_A + st * S::A_STAGE + sub * S::A_SLAB;
         const uint32_t a_lo = a_hi + TM * 128;
         if constexpr (MODE == MODE_GCL || MODE == MODE_EQUIV) {
           // ---- A = SiLU(P_i + Q_j + w_r r_ij + w_d d0_ij), packed fp32 pairs, shared reciprocals ---------------
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               Pc0 = __ldg(reinterpret_cast<const float4*>(pP[0] + k0));
               Pc1 = __ldg(reinterpret_cast<const float4*>(pP[0] + k0 + 4));
             }
-            if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
+            if (!waited) { mbar_wait(&a_empty[st], (((it / SPS) / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
               const int p = 2 * ph + pp;
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
                 v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
               }
             }
-            if (!waited) { mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
+            if (!waited) { mbar_wait(&a_empty[st], (((it / SPS) / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
               const int p = 2 * ph + pp;
@@ -491,9 +499,11 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
           }
         }
         TC_PROF(const long long tp2 = clock64();)
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) { if (crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+        if (sub == SPS - 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { if (crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+        }
         TC_PROF(tp_wait += tp1 - tp0; tp_comp += tp2 - tp1; tp_fence += clock64() - tp2;)
       }
     }
@@ -592,10 +602,13 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
                 for (int k = 0; k < GEOLDM_RES_BATCH; ++k) {
                   const int rl = (hb * GEOLDM_RES_BATCH + k) * 4 + orow_l;
                   const float4 t = lds128f(Tw + (rl * 36 + ocol) * 4);
-                  if (rl < nval)
-                    *reinterpret_cast<float4*>(a.out + (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol) =
+                  if (rl < nval) {
+                    const size_t goff = (size_t)(wrow0 + rl) * a.ldo + col0 + cc * 32 + ocol;
+                    *reinterpret_cast<float4*>(a.out + goff) =
                         make_float4(fmaf(t.x, scale, b4.x) + rs[k].x, fmaf(t.y, scale, b4.y) + rs[k].y,
                                     fmaf(t.z, scale, b4.z) + rs[k].z, fmaf(t.w, scale, b4.w) + rs[k].w);
+                    if (a.zero_buf) *reinterpret_cast<float4*>(a.zero_buf + goff) = make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
                 }
               }
             } else {
@@ -898,7 +911,9 @@ int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, co
 }
 
 int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
-                       int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st) {
+                       int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st,
+                       float* zero_buf) {
+  GEOLDM_REQUIRE(zero_buf == nullptr || epi == 2, "linear_tc16: zero_buf needs the residual epilogue (epi 2)");
   GEOLDM_REQUIRE(k1 % BK == 0 && k2 % BK == 0 && k1 + k2 > 0, "linear_tc16: k1=%d k2=%d must be multiples of %d", k1, k2, BK);
   GEOLDM_REQUIRE(w_pack != nullptr, "linear_tc16: w_pack missing");
   Args a{};
@@ -906,7 +921,7 @@ int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, 
   a.n_slabs = (k1 + k2) / BK;
   a.a1 = a1; a.a2 = a2; a.k1 = k1; a.k2 = k2; a.a2_div = a2_div;
   a.w_pack = reinterpret_cast<const uint8_t*>(w_pack);
-  a.b2 = bias; a.res = res; a.epi = epi; a.out = out; a.ldo = n_blocks * H;
+  a.b2 = bias; a.res = res; a.epi = epi; a.out = out; a.ldo = n_blocks * H; a.zero_buf = zero_buf;
   return launch_h<MODE_DENSE>(H, a, st);
 }
 

@@ -113,11 +113,12 @@ __global__ void outproj_kernel(int n_node, int H, int Fo, const float* __restric
 // the velocity at full precision (closer to the exact result, hence also closer to the reference: errors of
 // two fp32 evaluations add in quadrature).
 __global__ void coord_update_kernel(int n, const float* __restrict__ x0, const float* __restrict__ dx,
-                                    const float* __restrict__ xagg, float div, float* __restrict__ dx_next,
-                                    float* __restrict__ x_next) {
+                                    float* __restrict__ xagg, float div, float* __restrict__ dx_next,
+                                    float* __restrict__ x_next, bool zero_xagg) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   float a = xagg[k];
+  if (zero_xagg) xagg[k] = 0.f;          // consumed: ready for the next block's segment sums (no memset node)
   if (div != 1.0f) a = __fdiv_rn(a, div);
   const float d = dx ? __fadd_rn(dx[k], a) : a;
   dx_next[k] = d;
@@ -406,10 +407,10 @@ int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, float* u
   GEOLDM_CHECK_LAUNCH("edge_dist_kernel");
   return 0;
 }
-int launch_coord_update(int n3, const float* x0, const float* dx, const float* xagg, float div, float* dx_next,
-                        float* x_next, cudaStream_t st) {
+int launch_coord_update(int n3, const float* x0, const float* dx, float* xagg, float div, float* dx_next,
+                        float* x_next, cudaStream_t st, bool zero_xagg) {
   if (n3 == 0) return 0;
-  coord_update_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(n3, x0, dx, xagg, div, dx_next, x_next);
+  coord_update_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(n3, x0, dx, xagg, div, dx_next, x_next, zero_xagg);
   GEOLDM_CHECK_LAUNCH("coord_update_kernel");
   return 0;
 }
