@@ -35,16 +35,27 @@ def sample_sharded(args, device, generative_model, dataset_info, nodesxsample, c
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     nodes = torch.as_tensor(nodesxsample).cpu()
     B = len(nodes)
-    mine = shard_indices(nodes, world, rank)
-    ctx = None if context is None else context[torch.from_numpy(mine)]
-    one_hot, charges, x, node_mask = sample_fn(args, device, generative_model, dataset_info,
-                                               nodesxsample=nodes[torch.from_numpy(mine)], context=ctx,
-                                               fix_noise=fix_noise, seed=seed, mol_ids=mine)
+    shards = balance_shards(nodes.numpy(), world)            # computed once; identical on every rank
+    mine = shards[rank]
+    if len(mine) > 0:
+        ctx = None if context is None else context[torch.from_numpy(mine)]
+        one_hot, charges, x, node_mask = sample_fn(args, device, generative_model, dataset_info,
+                                                   nodesxsample=nodes[torch.from_numpy(mine)], context=ctx,
+                                                   fix_noise=fix_noise, seed=seed, mol_ids=mine)
     if world == 1:
         return one_hot, charges, x, node_mask
-    # pad every shard to the largest one, gather once, scatter back into the caller's order
-    sizes = [len(balance_shards(nodes.numpy(), world)[r]) for r in range(world)]
-    cap = max(sizes)
+    # pad every shard to the largest one, gather once, scatter back into the caller's order.  A rank whose shard is
+    # empty (more ranks than molecules) skips sampling and contributes all-padding payloads: the shapes and dtypes of
+    # the payload rows are broadcast from the first non-empty rank so that every rank issues the same collectives.
+    cap = max(len(s_) for s_ in shards)
+    first = next(r for r in range(world) if len(shards[r]) > 0)
+    meta = [None]
+    if rank == first:
+        meta = [[(tuple(t.shape[1:]), t.dtype) for t in (one_hot, charges, x, node_mask)]]
+    dist.broadcast_object_list(meta, src=first if group is None else dist.get_global_rank(group, first), group=group)
+    if len(mine) == 0:
+        dev_ = torch.device(device)
+        one_hot, charges, x, node_mask = (torch.zeros((0,) + shp, dtype=dt, device=dev_) for shp, dt in meta[0])
 
     def padded(t):
         out = t.new_zeros((cap,) + tuple(t.shape[1:]))
@@ -53,7 +64,8 @@ def sample_sharded(args, device, generative_model, dataset_info, nodesxsample, c
 
     idx = torch.full((cap,), -1, dtype=torch.int64, device=x.device)
     idx[:len(mine)] = torch.from_numpy(mine).to(x.device)
-    payload = [padded(one_hot), padded(charges) if charges.numel() else None, padded(x), padded(node_mask), idx]
+    has_charges = meta[0][1][0] != () and all(d > 0 for d in meta[0][1][0])     # include_charges=False -> empty charges
+    payload = [padded(one_hot), padded(charges) if has_charges else None, padded(x), padded(node_mask), idx]
     gathered = []
     for t in payload:
         if t is None:

@@ -53,6 +53,19 @@ def test_sharded_sampling_matches_single_rank(tmp_path):
     assert shards[0] | shards[1] == set(range(len(nodes))) and not (shards[0] & shards[1])
 
 
+def test_sharded_sampling_with_an_empty_rank(tmp_path):
+    """More ranks than molecules: the rank with an empty shard skips sampling and still takes part in the gather."""
+    nodes = [17]
+    port = 29950 + os.getpid() % 40
+    mp.spawn(_worker, args=(2, port, nodes, str(tmp_path)), nprocs=2, join=True)
+    info = {"max_n_nodes": 29}
+    ref = fake_sample(None, "cpu", None, info, nodesxsample=torch.tensor(nodes), seed=3, mol_ids=np.arange(1))
+    for r in range(2):
+        d = torch.load(os.path.join(tmp_path, f"r{r}.pt"), weights_only=False)
+        for got, want in zip(d["res"], ref):
+            assert torch.equal(got, want)
+
+
 # ---- training: gradient all-reduce over two ranks == single-rank gradients of the whole batch ----------------
 def _patch_cpu_autograd():
     """Route the wrappers through train.py's library-op graph so the host logic can run on CPU in this test."""

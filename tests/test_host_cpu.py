@@ -157,3 +157,21 @@ def test_product_distribution_nodes_matches_reference_draws():
     lp = nd.log_prob(torch.tensor([29, 9, 18]))
     idx = [list(QM9_WITH_H_N_NODES.keys()).index(k) for k in (29, 9, 18)]
     assert np.allclose(lp.numpy(), np.log(p[idx] / p.sum()), rtol=1e-6)
+
+
+def test_gradient_buckets_cover_every_trainable_parameter():
+    """training.gradient_buckets: latent model (decoder + denoiser; encoder too when the first stage is trainable) and a
+    stand-alone first-stage EnHierarchicalVAE ('encoder.*' / 'decoder.*' names) - no trainable parameter is left out,
+    so multi-rank training can never skip the all-reduce silently."""
+    from oracle import geoldm_oracle as O
+    from tests.helpers import make_args
+    from geoldm_b200.models import get_autoencoder, get_latent_diffusion
+    from geoldm_b200.training import gradient_buckets
+    cfg = O.OracleConfig(nf=32, n_layers=1)
+    info = {"atom_decoder": list(range(5)), "n_nodes": {5: 1}, "max_n_nodes": 29}
+    for build, kw in ((get_latent_diffusion, dict(trainable_ae=True)), (get_latent_diffusion, dict(trainable_ae=False)),
+                      (get_autoencoder, dict(trainable_ae=True))):
+        model = build(make_args(cfg, "fp32", **kw), "cpu", info, None)[0]
+        want = {id(p) for p in model.parameters() if p.requires_grad}
+        got = [id(p) for b in gradient_buckets(model) for p in b]
+        assert len(got) == len(set(got)) and set(got) == want and len(want) > 0, (build.__name__, kw)
