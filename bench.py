@@ -404,8 +404,8 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
     q.add(3000.0)
     model_ema = copy.deepcopy(model)
     ema = training.EMA(args.ema_decay)
-    buckets = training.gradient_buckets(model)
-    nbytes = sum(p.numel() * p.element_size() for b in buckets for p in b)
+    buckets = training.FlatGradBuckets(model)                  # flat per-bucket gradients, all-reduce overlapped with backward
+    nbytes = buckets.nbytes
     times = []
     for it in range(steps + 2):
         if dist is not None:

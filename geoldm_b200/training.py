@@ -105,16 +105,99 @@ def allreduce_gradients(buckets: Iterable[List[torch.nn.Parameter]], group=None)
     return total
 
 
+class FlatGradBuckets:
+    """Gradient buckets whose ``.grad`` tensors are VIEWS of one flat buffer per bucket (buckets in reverse
+    registration order, overlapped with backward).  Zeroing is one memset per bucket, the all-reduce runs on the flat
+    buffer itself (no flatten / unflatten copies), and a bucket's all-reduce is launched asynchronously from a
+    post-accumulate hook as soon as its last gradient has been produced, i.e. while backward is still working on the
+    earlier layers; ``finish`` waits for the collectives and averages.  The same object serves a single process
+    (no collective, only the cheap zeroing)."""
+
+    def __init__(self, model, group=None):
+        self.group = group
+        self.buckets = gradient_buckets(model)
+        self.flat, self._pending, self._works, self._hooks = [], [], [], []
+        for bi, params in enumerate(self.buckets):
+            n = sum(p.numel() for p in params)
+            flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+            off = 0
+            for p in params:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+            self.flat.append(flat)
+            self._pending.append(0)
+        self.nbytes = sum(f.numel() * f.element_size() for f in self.flat)
+        self._armed = False
+
+    def __iter__(self):          # usable wherever a list of parameter lists is expected
+        return iter(self.buckets)
+
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, bi):
+        def hook(param):
+            if not self._armed:
+                return
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0 and self._distributed():
+                self._works.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return hook
+
+    def zero(self):
+        """Replaces optim.zero_grad(): the views stay attached, the flat buffers are cleared."""
+        for bi, (flat, params) in enumerate(zip(self.flat, self.buckets)):
+            flat.zero_()
+            off = 0
+            for p in params:                  # re-attach views an optimiser / user may have dropped (set_to_none)
+                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + off * flat.element_size():
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._pending[bi] = len(params)
+        self._works = []
+        self._armed = True
+
+    def finish(self) -> int:
+        """After backward: launch what the hooks could not (parameters that received no gradient on this rank keep
+        their zeros; every rank issues the same collectives), wait, average.  Returns the bytes all-reduced."""
+        self._armed = False
+        if not self._distributed():
+            return 0
+        for bi, flat in enumerate(self.flat):
+            if self._pending[bi] != 0:
+                self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                self._pending[bi] = 0
+        for w in self._works:
+            w.wait()
+        world = dist.get_world_size(self.group)
+        for flat in self.flat:
+            flat.div_(world)
+        self._works = []
+        return self.nbytes
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def train_step(args, model, optim, nodes_dist, x, h, node_mask, edge_mask, context, *, gradnorm_queue: Optional[Queue],
                model_ema=None, ema: Optional[EMA] = None, buckets=None, group=None, draws=None):
     """One iteration of train_test.py:train_epoch on this rank's shard.  Returns (nll, grad_norm)."""
     model.train()
-    optim.zero_grad(set_to_none=True)
+    flat = buckets if isinstance(buckets, FlatGradBuckets) else None
+    if flat is not None:
+        flat.zero()                       # gradients live in flat per-bucket buffers; all-reduce overlaps backward
+    else:
+        optim.zero_grad(set_to_none=True)
     nll, reg_term, _ = losses.compute_loss_and_nll(args, model, nodes_dist, x, h, node_mask, edge_mask, context,
                                                    draws=draws)
     loss = nll + getattr(args, "ode_regularization", 0.0) * reg_term.squeeze()
     loss.backward()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if flat is not None:
+        flat.finish()
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         allreduce_gradients(buckets if buckets is not None else gradient_buckets(model), group)
     grad_norm = 0.
     if getattr(args, "clip_grad", True) and gradnorm_queue is not None:

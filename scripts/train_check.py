@@ -102,6 +102,7 @@ def main():
     model.zero_grad(set_to_none=True)
     # ---- timed steps --------------------------------------------------------------------------------------------------
     optim = training.get_optim(args, model)
+    buckets = training.FlatGradBuckets(model)      # timed steps: flat gradients, all-reduce overlapped with backward
     q = training.Queue()
     q.add(3000.0)
     model_ema = copy.deepcopy(model)

@@ -94,8 +94,8 @@ def _train_setup():
     return model, DistributionNodes(HISTOGRAMS["qm9"]), data, args
 
 
-def _step(model, nodes_dist, data, args, idx):
-    from geoldm_b200.training import Queue, get_optim, train_step
+def _step(model, nodes_dist, data, args, idx, flat=False):
+    from geoldm_b200.training import FlatGradBuckets, Queue, get_optim, train_step
     q = Queue()
     q.add(3000.0)
     optim = get_optim(args, model)
@@ -103,25 +103,29 @@ def _step(model, nodes_dist, data, args, idx):
     pick = lambda t: t[idx]
     h = {"categorical": pick(data["one_hot"]), "integer": pick(data["charges"])}
     em = pick(data["em"]).reshape(-1, 1)
+    buckets = FlatGradBuckets(model) if flat else None      # flat: all-reduce launched from backward hooks (overlap)
     nll, gn = train_step(args, model, optim, nodes_dist, pick(data["x"]), h, pick(data["nm"]), em, None,
-                         gradnorm_queue=q, draws={k: pick(v) for k, v in data["draws"].items()})
+                         gradnorm_queue=q, draws={k: pick(v) for k, v in data["draws"].items()}, buckets=buckets)
     return nll, float(gn)
 
 
-def _train_worker(rank, world, port, out_dir):
+def _train_worker(rank, world, port, out_dir, flat):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     _patch_cpu_autograd()
     model, nodes_dist, data, args = _train_setup()
-    nll, gn = _step(model, nodes_dist, data, args, [2 * rank, 2 * rank + 1])
+    nll, gn = _step(model, nodes_dist, data, args, [2 * rank, 2 * rank + 1], flat)
     torch.save({"sd": model.state_dict(), "gn": gn, "nll": nll}, os.path.join(out_dir, f"t{rank}.pt"))
     dist.destroy_process_group()
 
 
-def test_two_rank_training_step_matches_single_rank(tmp_path, monkeypatch):
-    port = 29950 + os.getpid() % 40
-    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("flat", [False, True])
+def test_two_rank_training_step_matches_single_rank(tmp_path, monkeypatch, flat):
+    """flat=False: one all-reduce per bucket after backward; flat=True: FlatGradBuckets (gradients are views of flat
+    buffers, all-reduces launched from post-accumulate hooks while backward runs)."""
+    port = 29950 + os.getpid() % 40 + (50 if flat else 0)
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path), flat), nprocs=2, join=True)
     from geoldm_b200 import dynamics
     from geoldm_b200 import train as _train
     monkeypatch.setattr(_train, "_CPU_GRAPH_CHECK", True)
