@@ -44,13 +44,14 @@ class EgnnWeights(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_mol", C.c_int), ("n_node", C.c_int), ("n_edge", C.c_int), ("n_tile", C.c_int),
                 ("tile_m", C.c_int), ("mol_off", fp), ("node_mol", fp), ("edge_i", fp), ("edge_j", fp),
-                ("tile_row", fp)]
+                ("tile_row", fp), ("tile_meta", fp)]
 
 
 _SIGS = {
     "geoldm_abi_version": (C.c_int, []),
     "geoldm_last_error": (C.c_char_p, []),
     "geoldm_has_tcgen05": (C.c_int, []),
+    "geoldm_batch_tile_meta": (C.c_int, [C.POINTER(Batch), fp, fp]),
     "geoldm_egnn_workspace_bytes": (C.c_size_t, [C.POINTER(EgnnConfig), C.c_int, C.c_int]),
     "geoldm_egnn_forward": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EgnnWeights), C.POINTER(Batch), fp, fp, fp, fp,
                                       fp, fp, C.c_size_t, fp]),
@@ -109,7 +110,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.geoldm_abi_version() != 3:
+        if handle.geoldm_abi_version() != 4:
             raise GeoldmError("ABI version mismatch between _lib.py and libgeoldm_b200.so")
         _lib = handle
     return _lib

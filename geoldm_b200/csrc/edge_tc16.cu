@@ -12,8 +12,12 @@
 // it keeps w_lo out of the fp16 subnormal range; the epilogue folds 2^-e into the round-toward-zero compensation
 // factor.  Activations are not scaled: |a| < 65504 is required for full accuracy (larger values saturate, they do not become
 // inf / NaN); a_lo below 2^-14 is subnormal: absolute error <= 2^-25.
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <limits.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -35,6 +39,11 @@ using namespace tc;
 
 constexpr int TM = 128;          // rows per tile (TMEM lanes)
 constexpr int BK = 64;           // k-slab: 64 fp16 = 128 bytes per row = one swizzle row
+// K order inside a slab: the 16-byte operand chunk c (8 fp16) holds the slab's columns 4c..4c+3 and 32+4c..32+4c+3, in the
+// A images and in the packed W images alike (a common K permutation leaves the product unchanged).  A producer thread
+// then reads two 16-byte pieces that are 128 bytes apart and the 8 chunk-lanes of a row cover one contiguous 128-byte
+// line per load instruction (half the L1 wavefronts of the 32-bytes-per-lane order).
+constexpr int KH = BK / 2;
 #ifndef GEOLDM_EQUIV_SPS
 #define GEOLDM_EQUIV_SPS 1
 #endif
@@ -57,6 +66,9 @@ struct Roles {
   static constexpr int NHALF = EPI_W / 4;                     // column halves split over distinct epilogue warps
 };
 constexpr int MODE_GCL = 0, MODE_EQUIV = 1, MODE_DENSE = 2, MODE_RAW = 3;
+// per-tile staging of the first-layer projections (TMA tensor copies): one box of STAGE_PBOX receiver rows and one of
+// STAGE_QBOX sender rows x 64 fp32 columns per k-slab
+constexpr uint32_t STAGE_PBOX = 16, STAGE_QBOX = 64;
 constexpr uint32_t PACK_HDR = 128;   // bytes: float inv_scale at offset 0
 constexpr float RZ_BIAS_PER_MMA = 1.60e-8f;   // see edge_tc.cu (round-toward-zero accumulation of the tensor core)
 
@@ -71,6 +83,7 @@ struct Args {
   const float* w_rd;
   const float* r_edge; const float* d0_edge;   // [E] precomputed squared distances (or null: computed from x / x0)
   const float4* u_edge;                        // [E] precomputed (x_i - x_j) / (|x_i - x_j| + c) (or null)
+  const int4* tile_meta;                       // [n_tile] {first receiver, first sender, staged, 0} (or null: gather path)
   const float* a1; const float* a2; int k1, k2; float a2_div;
   const uint8_t* w_pack;    // header + [block][slab][N-half][hi image | lo image]
   const float* b2; const float* w_out; const float* b_out; const float* res;
@@ -87,7 +100,10 @@ struct Smem {
   // EQUIV has no transposition tiles and can spend that shared memory on two-slab A stages (half the hand-offs per tile).
   static constexpr int SPS = (MODE == 1 && (H / 64) % 2 == 0) ? GEOLDM_EQUIV_SPS : 1;
   static constexpr int NAS = (MODE == 1) ? (SPS == 2 ? 2 : 3) : 2;
-  static constexpr int NWS = (SPS == 2) ? 2 : 3;
+#ifndef GEOLDM_EDGE_NWS
+#define GEOLDM_EDGE_NWS 2
+#endif
+  static constexpr int NWS = (SPS == 2) ? 2 : ((MODE <= 1) ? GEOLDM_EDGE_NWS : 3);
   // warp-private [32 rows][36 floats] transposition tiles: GCL 8 warps (segment sum), DENSE / RAW 4 warps (coalesced
   // output rows); EQUIV needs none
   static constexpr uint32_t T_BYTES = (MODE == 1) ? 0u : 8u * 32 * 36 * 4;
@@ -98,7 +114,11 @@ struct Smem {
   static constexpr uint32_t A_STAGE = SPS * A_SLAB;
   static constexpr uint32_t OFF_W = 0;
   static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;
-  static constexpr uint32_t OFF_T = OFF_A + NAS * A_STAGE;
+  // staged first-layer projections (edge modes): NPS stages of [STAGE_PBOX + STAGE_QBOX rows][64 fp32], filled by TMA
+  static constexpr int NPS = (MODE <= 1) ? 2 : 0;
+  static constexpr uint32_t PQ_STAGE = (STAGE_PBOX + STAGE_QBOX) * 256u;
+  static constexpr uint32_t OFF_PQ = OFF_A + NAS * A_STAGE;
+  static constexpr uint32_t OFF_T = OFF_PQ + NPS * PQ_STAGE;
   static constexpr uint32_t OFF_SI = OFF_T + T_BYTES;
   static constexpr uint32_t OFF_PS = OFF_SI + TM * 4;
   static constexpr uint32_t OFF_DX = OFF_PS + 8 * 34 * 4;
@@ -106,7 +126,7 @@ struct Smem {
   static constexpr uint32_t OFF_VEC = OFF_DOT + 2 * TM * 4;
   static constexpr uint32_t OFF_WRD = OFF_VEC + 2 * H * 4;    // float [2][H]: distance columns of the first edge layer
   static constexpr uint32_t OFF_BAR = OFF_WRD + 2 * H * 4;
-  static constexpr uint32_t OFF_TMEM = OFF_BAR + (3 * NWS + 2 * NAS + 4) * 8;
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + (3 * NWS + 2 * NAS + 4 + 2 * NPS) * 8;
   static constexpr uint32_t BYTES = OFF_TMEM + 16;
   static constexpr uint32_t ALLOC = BYTES + 1024;
 };
@@ -160,12 +180,13 @@ __device__ __forceinline__ void split_f16x2(f32x2 e, uint32_t& hi, uint32_t& lo)
 }
 
 template <int H, int MODE>
-__global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Args a) {
+__global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Args a, const __grid_constant__ CUtensorMap tm_p,
+                                                                        const __grid_constant__ CUtensorMap tm_q) {
   using S = Smem<H, MODE>;
   using R = Roles<MODE>;
   constexpr int NTHREADS = R::NTHREADS, EPI_T = R::EPI_T, WARP_LOAD = R::WARP_LOAD, WARP_MMA = R::WARP_MMA;
   constexpr int ROWS_PT = R::ROWS_PT, NHALF = R::NHALF;
-  constexpr int NAS = S::NAS, NWS = S::NWS, SPS = S::SPS;
+  constexpr int NAS = S::NAS, NWS = S::NWS, SPS = S::SPS, NPS = S::NPS > 0 ? S::NPS : 1;   // (NPS: no zero divisor in dead code)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -176,6 +197,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
   uint64_t* acc_full = bars + 2 * NWS + 2 * NAS;      // [2]  accumulator region r holds a complete tile
   uint64_t* acc_empty = bars + 2 * NWS + 2 * NAS + 2; // [2]  region r drained by the epilogue
   uint64_t* w_peer = bars + 2 * NWS + 2 * NAS + 4;    // [NWS] the peer CTA's N-half of the W stage has landed
+  uint64_t* pq_full = bars + 3 * NWS + 2 * NAS + 4;   // [NPS] staged projection rows of a k-slab have landed (TMA)
+  uint64_t* pq_empty = pq_full + NPS;                 // [NPS] ... have been read by every producer warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
 
   TC_PROF(const long long t_entry = clock64();)
@@ -194,6 +217,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
     for (int s = 0; s < NWS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&w_peer[s], 1); }
     for (int s = 0; s < NAS; ++s) { mbar_init(&a_full[s], 2 * R::PROD_W); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * R::EPI_W); }
+    for (int s = 0; s < S::NPS; ++s) { mbar_init(&pq_full[s], 1); mbar_init(&pq_empty[s], R::PROD_W); }
     fence_barrier_init();
   }
   if (warp == WARP_MMA) tmem_alloc2(tmem_slot, 512);
@@ -230,9 +254,33 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
     nrows = (a.tile_row ? a.tile_row[tile + 1] : min(a.n_rows, row0 + TM)) - row0;
   };
 
+  // staging decision of a tile (edge modes): all its receivers / senders inside the two TMA boxes
+  auto meta_of = [&](int tile, int nrows) -> int4 {
+    if ((MODE == MODE_GCL || MODE == MODE_EQUIV) && a.tile_meta != nullptr && nrows > 0) return __ldg(a.tile_meta + tile);
+    return make_int4(0, 0, 0, 0);
+  };
+
   if (warp == WARP_LOAD) {
     // =========================== W-stage loader (TMA engine) ==============================================
-    if (lane == 0) {
+    if ((MODE == MODE_GCL || MODE == MODE_EQUIV) && lane == 2 && a.tile_meta != nullptr) {
+      // staged projections: per k-slab one tensor copy of the tile's receiver rows (P columns) and one of its sender
+      // rows (Q columns); rows past the end of the tensor are zero-filled by the TMA unit
+      uint32_t pit = 0;
+      for (int iter = 0; iter < n_iter; ++iter) {
+        int tile, nb, row0, nrows;
+        tile_of(iter, tile, nb, row0, nrows);
+        const int4 m = meta_of(tile, nrows);
+        if (!m.z) continue;
+        for (int s = 0; s < H / BK; ++s, ++pit) {
+          const int st = pit % NPS;
+          mbar_wait(&pq_empty[st], ((pit / NPS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&pq_full[st], S::PQ_STAGE);
+          uint8_t* dst = smem + S::OFF_PQ + st * S::PQ_STAGE;
+          tma_load_2d(dst, &tm_p, s * BK, m.x, &pq_full[st]);
+          tma_load_2d(dst + STAGE_PBOX * 256u, &tm_q, H + s * BK, m.y, &pq_full[st]);
+        }
+      }
+    } else if (lane == 0) {
       uint32_t wit = 0;
       for (int iter = 0; iter < n_iter; ++iter) {
         int tile, nb, row0, nrows;
@@ -313,7 +361,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
     const int pt = tid - EPI_T;
     const int chunk = pt & 7;
     const int rg = pt >> 3;
-    uint32_t it = 0;
+    uint32_t it = 0, pit = 0;
     TC_PROF(long long tp_wait = 0; long long tp_comp = 0; long long tp_fence = 0; long long tp_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
       TC_PROF(const long long tm0 = clock64();)
@@ -321,9 +369,12 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       tile_of(iter, tile, nb, row0, nrows);
       const float* pP[ROWS_PT];
       const float* pQ[ROWS_PT];
+      uint32_t oP[ROWS_PT], oQ[ROWS_PT];   // staged tiles: byte offsets of the row's P / Q projections inside a stage
       float rr[ROWS_PT], dd[ROWS_PT];
       unsigned lmask = 0;                  // row needs a fresh P load (first row of the thread / receiver changed)
       int prev_i = -1;
+      const int4 meta = meta_of(tile, nrows);
+      const bool staged = meta.z != 0;
       // rows beyond the end of the tile are CLAMPED to its last row (an empty tile: row 0 of the launch): they produce
       // a copy of a real row, which the epilogue ignores (accumulator rows are independent) -> no validity branches,
       // every load unconditional and in bounds
@@ -332,18 +383,20 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
 #pragma unroll
       for (int p = 0; p < ROWS_PT; ++p) {
         const int grow = rbase0 + min(rg * ROWS_PT + p, rlast);
-        rr[p] = 0.f; dd[p] = 0.f; pQ[p] = nullptr;
+        rr[p] = 0.f; dd[p] = 0.f; pQ[p] = nullptr; oP[p] = 0; oQ[p] = 0;
         if (MODE == MODE_DENSE) {
-          pP[p] = a.a1 + (size_t)grow * a.k1 + 8 * chunk;
-          pQ[p] = a.a2 ? a.a2 + (size_t)grow * a.k2 + 8 * chunk : nullptr;
+          pP[p] = a.a1 + (size_t)grow * a.k1 + 4 * chunk;
+          pQ[p] = a.a2 ? a.a2 + (size_t)grow * a.k2 + 4 * chunk : nullptr;
         } else {
           const int i = a.edge_i[grow];
-          pP[p] = a.pq + (size_t)i * a.pq_ld + 8 * chunk;
+          pP[p] = a.pq + (size_t)i * a.pq_ld + 4 * chunk;
+          oP[p] = (uint32_t)(i - meta.x) * 256u + 16u * chunk;
           if (i != prev_i) lmask |= 1u << p;
           prev_i = i;
           if (MODE != MODE_RAW) {
             const int j = a.edge_j[grow];
-            pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 8 * chunk;
+            pQ[p] = a.pq + (size_t)j * a.pq_ld + H + 4 * chunk;
+            oQ[p] = (STAGE_PBOX + (uint32_t)(j - meta.y)) * 256u + 16u * chunk;
             if (a.r_edge) {
               rr[p] = __ldg(a.r_edge + grow);
               dd[p] = __ldg(a.d0_edge + grow);
@@ -366,6 +419,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         const int ntile = 2 * ((iter + 1) * n_workers + worker) + (int)crank;
         const int n2tile = ntile + 2 * n_workers;
         if (a.tile_row && n2tile < a.n_tile && pt == 0) prefetch_l1(a.tile_row + n2tile);   // tile_row two tiles ahead
+        if (a.tile_meta && ntile < a.n_tile && pt == 1) prefetch_l1(a.tile_meta + ntile);
         if (iter + 1 < n_iter && ntile < a.n_tile && chunk == 0) {
           const int nrow = (a.tile_row ? a.tile_row[ntile] : ntile * TM) + rg * ROWS_PT;
           if (nrow < a.n_rows) {
@@ -381,10 +435,27 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
       // immediate offset (no 64-bit address arithmetic per load)
       constexpr int KS_STATIC = H / BK;
       const int n_slabs_p = (MODE == MODE_DENSE) ? a.n_slabs : KS_STATIC;
+      auto run_slabs = [&](auto stg_tag) {
+      constexpr bool STG = decltype(stg_tag)::value;   // this tile's projection rows are staged in shared memory (TMA)
 #pragma unroll(MODE == MODE_DENSE ? 1 : KS_STATIC)
       for (int s = 0; s < n_slabs_p; ++s, ++it) {
         const int st = (it / SPS) % NAS, sub = it % SPS;
         const int k0 = s * BK;
+        uint32_t pqb = 0;
+        int pst = 0;
+        if constexpr (STG) {
+          pst = pit % NPS;
+          mbar_wait(&pq_full[pst], (pit / NPS) & 1);
+          pqb = sbase + S::OFF_PQ + pst * S::PQ_STAGE;
+        }
+        auto ld_p = [&](int p, int hsel) -> float4 {
+          if constexpr (STG) return lds128f(pqb + oP[p] + hsel * 128);
+          else return __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + hsel * KH));
+        };
+        auto ld_q = [&](int p, int hsel) -> float4 {
+          if constexpr (STG) return lds128f(pqb + oQ[p] + hsel * 128);
+          else return __ldg(reinterpret_cast<const float4*>(pQ[p] + k0 + hsel * KH));
+        };
         TC_PROF(const long long tp0 = clock64(); long long tp1 = tp0;)
         bool waited = sub != 0;                      // the stage was acquired with its first slab
         const uint32_t a_hi = sbase + S::OFF_A + st * S::A_STAGE + sub * S::A_SLAB;
@@ -393,9 +464,9 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
           // ---- A = SiLU(P_i + Q_j + w_r r_ij + w_d d0_ij), packed fp32 pairs, shared reciprocals ---------------
           f32x2 WR[4], WD[4];
           {
-            const uint32_t s_wrd = sbase + S::OFF_WRD + (k0 + 8 * chunk) * 4;
-            const float4 r0 = lds128f(s_wrd), r1 = lds128f(s_wrd + 16);
-            const float4 d0 = lds128f(s_wrd + H * 4), d1 = lds128f(s_wrd + H * 4 + 16);
+            const uint32_t s_wrd = sbase + S::OFF_WRD + (k0 + 4 * chunk) * 4;
+            const float4 r0 = lds128f(s_wrd), r1 = lds128f(s_wrd + KH * 4);
+            const float4 d0 = lds128f(s_wrd + H * 4), d1 = lds128f(s_wrd + H * 4 + KH * 4);
             WR[0] = pk2(r0.x, r0.y); WR[1] = pk2(r0.z, r0.w); WR[2] = pk2(r1.x, r1.y); WR[3] = pk2(r1.z, r1.w);
             WD[0] = pk2(d0.x, d0.y); WD[1] = pk2(d0.z, d0.w); WD[2] = pk2(d1.x, d1.y); WD[3] = pk2(d1.z, d1.w);
           }
@@ -415,12 +486,12 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
               const int p = 2 * ph + pp;
-              q[pp][0] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0));
-              q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + k0 + 4));
+              q[pp][0] = ld_q(p, 0);
+              q[pp][1] = ld_q(p, 1);
             }
             if (ph == 0) {
-              Pc0 = __ldg(reinterpret_cast<const float4*>(pP[0] + k0));
-              Pc1 = __ldg(reinterpret_cast<const float4*>(pP[0] + k0 + 4));
+              Pc0 = ld_p(0, 0);
+              Pc1 = ld_p(0, 1);
             }
             if (!waited) { mbar_wait(&a_empty[st], (((it / SPS) / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
 #pragma unroll
@@ -428,8 +499,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               const int p = 2 * ph + pp;
               const int r = rg * ROWS_PT + p;
               if (p > 0 && ((lmask >> p) & 1u)) {
-                Pc0 = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
-                Pc1 = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
+                Pc0 = ld_p(p, 0);
+                Pc1 = ld_p(p, 1);
               }
               uint4 hi, lo;
               const f32x2 R2 = pk2(rr[p], rr[p]), D2 = pk2(dd[p], dd[p]);
@@ -462,14 +533,14 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               if (MODE == MODE_DENSE) {
                 if (k0 < a.k1) {
                   v[pp][0] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
-                  v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
+                  v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + KH));
                 } else {
                   q[pp][0] = __ldg(reinterpret_cast<const float4*>(pQ[p] + (k0 - a.k1)));
-                  q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + (k0 - a.k1) + 4));
+                  q[pp][1] = __ldg(reinterpret_cast<const float4*>(pQ[p] + (k0 - a.k1) + KH));
                 }
               } else {
                 v[pp][0] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0));
-                v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + 4));
+                v[pp][1] = __ldg(reinterpret_cast<const float4*>(pP[p] + k0 + KH));
               }
             }
             if (!waited) { mbar_wait(&a_empty[st], (((it / SPS) / NAS) & 1) ^ 1); waited = true; TC_PROF(tp1 = clock64();) }
@@ -499,12 +570,23 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
           }
         }
         TC_PROF(const long long tp2 = clock64();)
+        if constexpr (STG) {                         // every lane's reads of the stage have returned (their values were used)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pq_empty[pst]);
+          ++pit;
+        }
         if (sub == SPS - 1) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) { if (crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
         }
         TC_PROF(tp_wait += tp1 - tp0; tp_comp += tp2 - tp1; tp_fence += clock64() - tp2;)
+      }
+      };
+      if constexpr (MODE == MODE_GCL || MODE == MODE_EQUIV) {
+        if (staged) run_slabs(std::true_type{}); else run_slabs(std::false_type{});
+      } else {
+        run_slabs(std::false_type{});
       }
     }
     TC_PROF(if (tid == EPI_T && blockIdx.x == 0) {
@@ -734,9 +816,68 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
           // 2 cp, 2 cp + 1 over every second row of the run (64-bit loads), the two halves are folded with one shuffle
           // and leave as one vector reduction per (run, column pair).  The summation order is fixed.
           const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);
-          const int half = lane >> 4, cp = lane & 15;
+          // Run structure of this warp's 32 rows, seen by lane (grp, c4): row group [8 grp, 8 grp + 8) x columns 4 c4 .. +3 of
+          // a chunk.  The first invalid row closes the last run (its "receiver" is -1: nothing is emitted for it).
+          const int grp = lane >> 3, c4 = lane & 7;
+          const unsigned hg = ((hm | (nval < 32 ? (1u << nval) : 0u)) >> (8 * grp)) & 0xFFu;
+          const unsigned inner = hg & 0xFEu;              // run boundaries strictly inside the group
+          // static path: at most one boundary inside every 8-row group (always true when runs are >= 8 rows long, i.e.
+          // molecules of >= 9 atoms); shorter runs take the generic loop below
+          const bool fast = __all_sync(0xffffffffu, __popc(inner) <= 1);
           uint32_t v[32];
           tmem_ld32(taddr, v);
+          if (fast) {
+            const int b = inner ? (__ffs(inner) - 1) : 8;                  // rows q < b: "lo" segment, q >= b: "hi" segment
+            const bool has_inner = inner != 0u;
+            const bool first_head = (hg & 1u) != 0u || grp == 0;           // the group's first row opens a run (of this warp)
+            const unsigned fhm = __ballot_sync(0xffffffffu, first_head);
+            const unsigned psm = __ballot_sync(0xffffffffu, !has_inner && !first_head);   // group lies inside one older run
+            const bool end_emit = grp == 3 || ((fhm >> (8 * (grp + 1))) & 1u) != 0u;     // the run open at the group's end closes
+            // carry-in = rows of the run containing row 8 grp that sit in earlier groups of this warp
+            const bool a1 = !first_head;
+            const bool a2 = a1 && grp >= 2 && ((psm >> (8 * (grp - 1))) & 1u) != 0u;
+            const bool a3 = a2 && grp >= 3 && ((psm >> (8 * (grp - 2))) & 1u) != 0u;
+            const int recv_lo = __shfl_sync(0xffffffffu, my_i, 8 * grp);
+            const int recv_hi = __shfl_sync(0xffffffffu, my_i, 8 * grp + 7);
+            const bool emit_lo = (has_inner || end_emit) && recv_lo >= 0;
+            const bool emit_hi = has_inner && end_emit && recv_hi >= 0;
+            float* const out_lo = a.out + (size_t)(recv_lo < 0 ? 0 : recv_lo) * H + hf * HC + 4 * c4;
+            float* const out_hi = a.out + (size_t)(recv_hi < 0 ? 0 : recv_hi) * H + hf * HC + 4 * c4;
+            const uint32_t tp = Tw + ((8 * grp) * 36 + 4 * c4) * 4;
+            const uint32_t tv = Tw + (lane * 36 + 32) * 4;                 // pad columns of row `lane`: carry exchange
+#pragma unroll 1
+            for (int cc = 0; cc < NCH; ++cc) {
+              tmem_ld_wait();
+              if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }
+#pragma unroll
+              for (int c4i = 0; c4i < 8; ++c4i) {
+                const f32x2 e01 = mul2(pk2(__uint_as_float(v[c4i * 4]), __uint_as_float(v[c4i * 4 + 1])), g2);
+                const f32x2 e23 = mul2(pk2(__uint_as_float(v[c4i * 4 + 2]), __uint_as_float(v[c4i * 4 + 3])), g2);
+                sts128p(Tw + (lane * 36 + c4i * 4) * 4, e01, e23);
+              }
+              if (cc + 1 < NCH) tmem_ld32(taddr + (cc + 1) * 32, v);   // in flight while the rows of this chunk are summed
+              __syncwarp();
+              f32x2 lo0 = pk2(0.f, 0.f), lo1 = lo0, hi0 = lo0, hi1 = lo0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                f32x2 t0, t1;
+                lds128p(tp + q * (36 * 4), t0, t1);
+                if (q < b) { lo0 = add2(lo0, t0); lo1 = add2(lo1, t1); }
+                else { hi0 = add2(hi0, t0); hi1 = add2(hi1, t1); }
+              }
+              // the segment still open at the end of the group, offered to the following groups
+              sts128p(tv, has_inner ? hi0 : lo0, has_inner ? hi1 : lo1);
+              __syncwarp();
+              f32x2 c0 = pk2(0.f, 0.f), c1 = c0;
+              if (a3) { f32x2 t0, t1; lds128p(tv - 24 * (36 * 4), t0, t1); c0 = t0; c1 = t1; }
+              if (a2) { f32x2 t0, t1; lds128p(tv - 16 * (36 * 4), t0, t1); c0 = add2(c0, t0); c1 = add2(c1, t1); }
+              if (a1) { f32x2 t0, t1; lds128p(tv - 8 * (36 * 4), t0, t1); c0 = add2(c0, t0); c1 = add2(c1, t1); }
+              if (emit_lo) red_add_v4p(out_lo + cc * 32, add2(c0, lo0), add2(c1, lo1));
+              if (emit_hi) red_add_v4p(out_hi + cc * 32, hi0, hi1);
+              __syncwarp();
+            }
+          } else {
+          const int half = lane >> 4, cp = lane & 15;
 #pragma unroll 1
           for (int cc = 0; cc < NCH; ++cc) {
             tmem_ld_wait();
@@ -776,6 +917,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
             }
             __syncwarp();
           }
+          }
           TC_PROF(te_p2 += clock64() - te4;)
           named_bar_sync(2 + (warp & 3), 64);
         }
@@ -798,8 +940,55 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
   TC_PROF(if (tid == 0 && blockIdx.x == 0) g_tc16_stats[15] += (unsigned long long)(clock64() - t_entry);)
 }
 
+// ---- TMA tensor maps over the [n_node][2H] projection matrix (row pitch pq_ld floats): boxes of 64 columns x box_rows rows.
+// cuTensorMapEncodeTiled is a host-only driver call (no device work); the maps of the last few (pointer, shape) combinations
+// are kept, a CUDA graph bakes them into its kernel nodes.
+struct StageMaps { CUtensorMap p, q; };
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_stage_maps(const float* pq, int pq_ld, int n_node, int H, StageMaps& out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("tc16: cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+      return -2;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  struct Key { const float* pq; int ld, n, H; };
+  static thread_local Key keys[8];
+  static thread_local StageMaps maps[8];
+  static thread_local int next = 0;
+  for (int k = 0; k < 8; ++k)
+    if (keys[k].pq == pq && keys[k].ld == pq_ld && keys[k].n == n_node && keys[k].H == H) { out = maps[k]; return 0; }
+  const cuuint64_t dims[2] = {(cuuint64_t)(2 * H), (cuuint64_t)n_node};
+  const cuuint64_t strides[1] = {(cuuint64_t)pq_ld * sizeof(float)};
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint32_t box_p[2] = {(cuuint32_t)BK, STAGE_PBOX}, box_q[2] = {(cuuint32_t)BK, STAGE_QBOX};
+  StageMaps m;
+  CUresult r1 = encode(&m.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pq), dims, strides, box_p, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = encode(&m.q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pq), dims, strides, box_q, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    set_error("tc16: cuTensorMapEncodeTiled failed (%d, %d) for pq=%p ld=%d n=%d", (int)r1, (int)r2, (const void*)pq, pq_ld, n_node);
+    return -2;
+  }
+  keys[next] = Key{pq, pq_ld, n_node, H};
+  maps[next] = m;
+  next = (next + 1) % 8;
+  out = m;
+  return 0;
+}
+
 template <int H, int MODE>
-int launch_mode(const Args& a, cudaStream_t st) {
+int launch_mode(const Args& a, cudaStream_t st, const StageMaps* sm = nullptr) {
   using S = Smem<H, MODE>;
   static int sm_count = 0;
   static bool configured = false;
@@ -836,7 +1025,9 @@ int launch_mode(const Args& a, cudaStream_t st) {
   if (pdl < 0) { const char* e = getenv("GEOLDM_TC_PDL"); pdl = e ? atoi(e) : 1; }
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc16_kernel<H, MODE>, args);
+  static const StageMaps no_maps{};
+  if (!sm) { sm = &no_maps; args.tile_meta = nullptr; }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc16_kernel<H, MODE>, args, sm->p, sm->q);
   if (e != cudaSuccess) {
     set_error("tc16_kernel launch: %s", cudaGetErrorString(e));
     return -2;
@@ -845,12 +1036,12 @@ int launch_mode(const Args& a, cudaStream_t st) {
 }
 
 template <int MODE>
-int launch_h(int H, const Args& a, cudaStream_t st) {
+int launch_h(int H, const Args& a, cudaStream_t st, const StageMaps* sm = nullptr) {
   switch (H) {
-    case 64: return launch_mode<64, MODE>(a, st);
-    case 128: return launch_mode<128, MODE>(a, st);
-    case 192: return launch_mode<192, MODE>(a, st);
-    case 256: return launch_mode<256, MODE>(a, st);
+    case 64: return launch_mode<64, MODE>(a, st, sm);
+    case 128: return launch_mode<128, MODE>(a, st, sm);
+    case 192: return launch_mode<192, MODE>(a, st, sm);
+    case 256: return launch_mode<256, MODE>(a, st, sm);
     default: set_error("tcgen05 kernels support hidden_nf 64/128/192/256, got %d", H); return -1;
   }
 }
@@ -876,7 +1067,8 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
   if (idx == 0) *reinterpret_cast<float*>(pack) = ldexpf(1.0f, -e);
   if (idx >= (size_t)n_out * k) return;
   const int n = (int)(idx / k), kk = (int)(idx % k);
-  const int nb = n / H, nl = n % H, slab = kk / 64, kl = kk % 64;
+  const int nb = n / H, nl = n % H, slab = kk / 64, ko = kk % 64;
+  const int kl = 8 * ((ko & 31) >> 2) + (ko & 3) + 4 * (ko >> 5);   // position inside the slab after the K permutation
   const int n_slabs = k / 64;
   const float v = w[idx] * scale;                                   // exact (power of two)
   const __half hi = __float2half_rn(v);
@@ -887,6 +1079,32 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
   uint8_t* img = pack + PACK_HDR + (size_t)((nb * n_slabs + slab) * 2 + half) * 2 * (size_t)NH * 128;
   *reinterpret_cast<__half*>(img + off) = hi;
   *reinterpret_cast<__half*>(img + (size_t)NH * 128 + off) = lo;
+}
+// One warp per tile: {first receiver, first sender, staged, 0}.  Edge rows are sorted by (molecule, receiver, sender), so the
+// first / last row hold the extreme receivers; senders are scanned.
+__global__ void tile_meta_kernel(int n_tile, int tile_m, int n_edge, const int* __restrict__ tile_row,
+                                 const int* __restrict__ edge_i, const int* __restrict__ edge_j, int4* __restrict__ out) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tile >= n_tile) return;
+  const int r0 = tile_row ? tile_row[tile] : tile * tile_m;
+  const int r1 = tile_row ? tile_row[tile + 1] : min(n_edge, r0 + tile_m);
+  int jmin = INT_MAX, jmax = INT_MIN;
+  for (int r = r0 + lane; r < r1; r += 32) { const int j = edge_j[r]; jmin = min(jmin, j); jmax = max(jmax, j); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+    jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+  }
+  if (lane == 0) {
+    int4 m = make_int4(0, 0, 0, 0);
+    if (r1 > r0) {
+      const int ilo = edge_i[r0], ihi = edge_i[r1 - 1];
+      m.x = ilo; m.y = jmin;
+      m.z = (ihi - ilo < (int)STAGE_PBOX && jmax - jmin < (int)STAGE_QBOX && ihi >= ilo) ? 1 : 0;
+    }
+    out[tile] = m;
+  }
 }
 }  // namespace
 
@@ -907,7 +1125,17 @@ int launch_edge_tc16(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, co
   a.b2 = w.b2; a.w_out = w.w_out; a.b_out = w.b_out; a.out = out;
   a.norm_constant = cfg.norm_constant; a.coords_range = cfg.coords_range;
   a.attention = cfg.attention; a.use_tanh = cfg.tanh;
-  return equiv ? launch_h<MODE_EQUIV>(cfg.hidden_nf, a, st) : launch_h<MODE_GCL>(cfg.hidden_nf, a, st);
+  // per-tile staging of the projection rows through TMA when the batch carries the table (GEOLDM_TC_STAGE=0: gather path)
+  static int stage = -1;
+  if (stage < 0) { const char* e = getenv("GEOLDM_TC_STAGE"); stage = e ? atoi(e) : 1; }
+  StageMaps sm;
+  const StageMaps* smp = nullptr;
+  if (stage && b.tile_meta != nullptr && b.n_tile > 0 && (reinterpret_cast<uintptr_t>(pq) & 15) == 0 && pq_ld % 4 == 0) {
+    if (int rc = make_stage_maps(pq, pq_ld, b.n_node, cfg.hidden_nf, sm)) return rc;
+    a.tile_meta = reinterpret_cast<const int4*>(b.tile_meta);
+    smp = &sm;
+  }
+  return equiv ? launch_h<MODE_EQUIV>(cfg.hidden_nf, a, st, smp) : launch_h<MODE_GCL>(cfg.hidden_nf, a, st, smp);
 }
 
 int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
@@ -936,6 +1164,14 @@ int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* t
 }  // namespace geoldm
 
 extern "C" {
+int geoldm_batch_tile_meta(const geoldm_batch* b, int* out, void* stream) {
+  GEOLDM_REQUIRE(b != nullptr && out != nullptr, "batch_tile_meta: null argument");
+  if (b->n_tile == 0) return 0;
+  geoldm::tile_meta_kernel<<<(b->n_tile + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      b->n_tile, b->tile_m, b->n_edge, b->tile_row, b->edge_i, b->edge_j, reinterpret_cast<int4*>(out));
+  GEOLDM_CHECK_LAUNCH("tile_meta_kernel");
+  return 0;
+}
 /* debug (GEOLDM_TC_PROFILE builds): read + reset the 16 cycle counters of the fp16-split kernel; synchronises */
 int geoldm_tc16_read_stats(unsigned long long* host_out) {
   cudaDeviceSynchronize();

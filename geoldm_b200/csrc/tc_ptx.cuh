@@ -66,6 +66,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// 2-D tensor copy (TMA tensor map, UTMALDG): box at element coordinates (c0 = innermost, c1) -> dense rows in shared memory
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // multicast variant: the bytes land at the same shared-memory offset in every CTA of `cta_mask` and complete_tx is
 // signalled on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
@@ -246,6 +255,20 @@ __device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
 // out[0] += a, out[1] += b as ONE vector reduction (8-byte aligned global address; fire and forget)
 __device__ __forceinline__ void red_add_v2(float* out, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(out), "f"(a), "f"(b) : "memory");
+}
+// 16 bytes of shared memory as two packed fp32 pairs
+__device__ __forceinline__ void lds128p(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts128p(uint32_t addr, unsigned long long a, unsigned long long b) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
+// out[0..3] += the four fp32 of two packed pairs as ONE vector reduction (16-byte aligned global address)
+__device__ __forceinline__ void red_add_v4p(float* out, unsigned long long a, unsigned long long b) {
+  float a0, a1, b0, b1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(b));
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(a0), "f"(a1), "f"(b0), "f"(b1) : "memory");
 }
 __device__ __forceinline__ float lds32f(uint32_t addr) {
   float v;

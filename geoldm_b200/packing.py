@@ -10,6 +10,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Sequence
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -61,8 +63,15 @@ class RaggedBatch:
             tile_row = torch.from_numpy(rows).to(self.device)
             cb = _lib.Batch(self.n_mol, self.n_node, self.n_edge, n_tile, tile_m, _lib.ptr(self.mol_off).value,
                             _lib.ptr(self.node_mol).value, _lib.ptr(self.edge_i).value, _lib.ptr(self.edge_j).value,
-                            _lib.ptr(tile_row).value)
-            self._tiles[tile_m] = (cb, tile_row)
+                            _lib.ptr(tile_row).value, None)
+            tile_meta = None
+            if tile_m == 128 and n_tile > 0 and self.device.type == "cuda":
+                # staging table of the tcgen05 edge kernels (first receiver / sender of every tile), built on the device
+                tile_meta = torch.empty(n_tile, 4, dtype=torch.int32, device=self.device)
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                _lib.check(_lib.lib().geoldm_batch_tile_meta(C.byref(cb), _lib.ptr(tile_meta), C.c_void_p(stream)), "batch_tile_meta")
+                cb.tile_meta = _lib.ptr(tile_meta).value
+            self._tiles[tile_m] = (cb, tile_row, tile_meta)
         return self._tiles[tile_m][0]
 
     def edge_messages(self) -> int:

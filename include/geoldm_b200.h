@@ -28,7 +28,7 @@ extern "C" {
 
 #define GEOLDM_MAX_LAYERS 16
 #define GEOLDM_MAX_SUBLAYERS 4
-#define GEOLDM_ABI_VERSION 3
+#define GEOLDM_ABI_VERSION 4
 
 /* arithmetic mode of the 256x256 edge/node contractions */
 enum {
@@ -106,7 +106,16 @@ typedef struct {
   const int* edge_i;         /* [n_edge]  receiver (aggregation index, `row`)               */
   const int* edge_j;         /* [n_edge]  sender (`col`)                                    */
   const int* tile_row;       /* [n_tile+1] first edge row of each tile; rows per tile <= tile_m */
+  const int* tile_meta;      /* [n_tile][4] {first receiver, first sender, staged flag, 0} written by
+                              * geoldm_batch_tile_meta (ABI v4), or NULL: the tcgen05 edge kernels then gather the
+                              * projection rows per edge instead of staging them per tile through TMA          */
 } geoldm_batch;
+
+/* Per-tile staging table of the tcgen05 edge kernels (ABI v4).  For every tile of b->tile_m edge rows: the first
+ * receiver and the first sender node it touches, and whether all its receivers / senders lie inside the boxes
+ * (16 / 64 consecutive nodes) that one TMA tensor copy per k-slab brings into shared memory.  b->tile_meta is ignored
+ * on input; `out` ([n_tile][4] int32, device) is what the caller stores there afterwards. */
+int geoldm_batch_tile_meta(const geoldm_batch* b, int* out, void* stream);
 
 int geoldm_abi_version(void);
 const char* geoldm_last_error(void);

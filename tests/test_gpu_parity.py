@@ -59,7 +59,7 @@ def cuda_masks(nodes, n_max, dev):
 # ---------------------------------------------------------------------------------------------------
 def test_library_is_the_cuda_build(dev):
     from geoldm_b200 import _lib
-    assert _lib.lib().geoldm_abi_version() == 3
+    assert _lib.lib().geoldm_abi_version() == 4
 
 
 @pytest.mark.parametrize("m,k1,k2,n,epi", [(1154, 256, 0, 512, 0), (1154, 256, 256, 256, 1), (333, 192, 0, 192, 2),

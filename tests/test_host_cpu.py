@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(handle, name), f"{name} declared in include/geoldm_b200.h but not exported"
     from geoldm_b200 import _lib
     assert set(_lib.EXPORTS) == declared, set(_lib.EXPORTS) ^ declared
-    assert _lib.lib().geoldm_abi_version() == 3
+    assert _lib.lib().geoldm_abi_version() == 4
 
 
 def test_product_has_no_cpu_fallback():
