@@ -58,7 +58,10 @@ struct Roles {
 #define GEOLDM_GCL_PROD_W 8
 #endif
   static constexpr int EPI_W = 8;
-  static constexpr int PROD_W = (MODE == 0) ? GEOLDM_GCL_PROD_W : 16;
+#ifndef GEOLDM_EQUIV_PROD_W
+#define GEOLDM_EQUIV_PROD_W 16
+#endif
+  static constexpr int PROD_W = (MODE == 0) ? GEOLDM_GCL_PROD_W : (MODE == 1) ? GEOLDM_EQUIV_PROD_W : 16;
   static constexpr int WARP_LOAD = EPI_W + PROD_W, WARP_MMA = WARP_LOAD + 1;
   static constexpr int NTHREADS = 32 * (EPI_W + PROD_W + 2);
   static constexpr int EPI_T = 32 * EPI_W;
