@@ -399,13 +399,14 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
     ctx = torch.randn(bs, 1, 1, generator=gen).to(dev).expand(-1, 29, -1) * nm
     h = {"categorical": one_hot, "integer": torch.zeros(0, device=dev)}
     x_host = x.cpu().pin_memory()
-    optim = training.get_optim(args, model)
-    q = training.Queue()
-    q.add(3000.0)
+    optim = training.get_optim(args, model, capturable=True)
     model_ema = copy.deepcopy(model)
     ema = training.EMA(args.ema_decay)
     buckets = training.FlatGradBuckets(model)                  # flat per-bucket gradients, all-reduce overlapped with backward
     nbytes = buckets.nbytes
+    # the whole step (loss, backward, bucketed all-reduce, device-side adaptive clipping, AdamW, EMA) as ONE captured graph
+    step = training.GraphedTrainStep(args, model, optim, nodes_dist, x, h, nm, em, ctx, model_ema=model_ema, ema=ema,
+                                     buckets=buckets)
     times = []
     for it in range(steps + 2):
         if dist is not None:
@@ -413,9 +414,7 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        xb = x_host.to(dev, non_blocking=True)                 # the step's positions arrive from pinned host memory
-        nll, gn = training.train_step(args, model, optim, nodes_dist, xb, h, nm, em, ctx, gradnorm_queue=q,
-                                      model_ema=model_ema, ema=ema, buckets=buckets)
+        nll, gn = step(x_host)                                 # the step's positions arrive from pinned host memory
         e1.record()
         torch.cuda.synchronize()
         if it >= 2:
@@ -425,7 +424,8 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     return {"workload": "BASELINE.json configs[4]: conditional QM9 GeoLDM training step, nf=192 n_layers=9, 64 molecules "
-                        "per GPU, trainable first stage, AdamW + EMA, gradient all-reduce over NCCL",
+                        "per GPU, trainable first stage, AdamW + EMA, gradient all-reduce over NCCL; the step is one captured CUDA graph "
+                        "(training.GraphedTrainStep)",
             "molecules_per_gpu": bs, "n_gpus": world, "ms_per_step": ms, "molecules_per_s": world * bs / (ms * 1e-3),
             "allreduce_bytes_per_step": nbytes if world > 1 else 0, "last_nll": float(nll), "finite": bool(torch.isfinite(nll))}
 

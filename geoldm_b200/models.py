@@ -23,6 +23,7 @@ class DistributionNodes:
         prob = np.array(list(histogram.values()), dtype=np.float64)
         prob = prob / np.sum(prob)
         self.prob = torch.from_numpy(prob).float()
+        self._lut = {}
         self.m = Categorical(torch.tensor(prob))
 
     def sample(self, n_samples=1):
@@ -30,6 +31,15 @@ class DistributionNodes:
 
     def log_prob(self, batch_n_nodes):
         assert batch_n_nodes.dim() == 1
+        if batch_n_nodes.is_cuda:
+            # device lookup table indexed by the atom count (no per-molecule host read, CUDA-graph capturable); a count
+            # outside the histogram, a KeyError in the reference, reads as NaN here
+            lut = self._lut.get(batch_n_nodes.device)
+            if lut is None:
+                host = torch.full((int(self.n_nodes.max()) + 1,), float("nan"))
+                host[self.n_nodes] = torch.log(self.prob + 1e-30)
+                lut = self._lut[batch_n_nodes.device] = host.to(batch_n_nodes.device)
+            return lut[batch_n_nodes.clamp(max=lut.numel() - 1)].masked_fill(batch_n_nodes >= lut.numel(), float("nan"))
         idcs = torch.tensor([self.keys[int(i)] for i in batch_n_nodes], device=batch_n_nodes.device)
         return torch.log(self.prob + 1e-30).to(batch_n_nodes.device)[idcs]
 

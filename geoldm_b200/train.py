@@ -235,7 +235,7 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
 
 def _remove_mean_ragged(v, batch: RaggedBatch):
     mol = batch.node_mol.long()
-    cnt = torch.as_tensor(batch.n_nodes, device=v.device, dtype=v.dtype).unsqueeze(1)
+    cnt = (batch.mol_off[1:] - batch.mol_off[:-1]).to(v.dtype).unsqueeze(1)          # device table: no host copy
     mean = torch.zeros(batch.n_mol, v.shape[1], device=v.device, dtype=v.dtype).index_add_(0, mol, v) / cnt
     return v - mean.index_select(0, mol)
 

@@ -65,9 +65,49 @@ def gradient_clipping(flow, gradnorm_queue: Queue):
     return grad_norm
 
 
-def get_optim(args, generative_model):
-    """qm9/models.py:169-175."""
-    return torch.optim.AdamW(generative_model.parameters(), lr=args.lr, amsgrad=True, weight_decay=1e-12)
+def get_optim(args, generative_model, capturable: bool = False):
+    """qm9/models.py:169-175.  `capturable=True`: step counters live on the device, so that the optimiser step can be part
+    of a captured CUDA graph (GraphedTrainStep)."""
+    return torch.optim.AdamW(generative_model.parameters(), lr=args.lr, amsgrad=True, weight_decay=1e-12,
+                             capturable=capturable)
+
+
+class DeviceGradClip:
+    """utils.py:29-66 (Queue + gradient_clipping) with the history on the DEVICE: the last 50 gradient norms in a ring
+    buffer, threshold 1.5 mean + 2 std (population std, as np.std), clip coefficient max_norm / (norm + 1e-6) clamped to 1
+    (torch.nn.utils.clip_grad_norm_), and the queue receives the threshold instead of the norm when clipping happened.
+    No host read: usable inside a captured CUDA graph."""
+
+    def __init__(self, device, max_len=50, first=3000.0):
+        self.hist = torch.zeros(max_len, device=device)
+        self.count = torch.zeros((), dtype=torch.long, device=device)
+        self.pos = torch.zeros((), dtype=torch.long, device=device)
+        self.max_len = max_len
+        self._idx = torch.arange(max_len, device=device)
+        self.add(torch.tensor(float(first), device=device))
+
+    def add(self, value):
+        self.hist.index_copy_(0, self.pos.reshape(1), value.reshape(1).to(self.hist.dtype))
+        self.pos.copy_((self.pos + 1) % self.max_len)
+        self.count.copy_(torch.clamp(self.count + 1, max=self.max_len))
+
+    def threshold(self):
+        valid = (self._idx < self.count).to(self.hist.dtype)
+        n = self.count.to(self.hist.dtype)
+        mean = (self.hist * valid).sum() / n
+        var = (((self.hist - mean) ** 2) * valid).sum() / n
+        return 1.5 * mean + 2.0 * var.sqrt()
+
+    @torch.no_grad()
+    def clip_(self, grads):
+        """grads: list of gradient tensors (e.g. the flat bucket buffers).  Returns the total norm (device scalar)."""
+        max_norm = self.threshold()
+        norms = torch._foreach_norm(grads, 2.0)
+        total = torch.linalg.vector_norm(torch.stack(norms), 2.0)
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        torch._foreach_mul_(grads, coef)
+        self.add(torch.where(total > max_norm, max_norm, total))
+        return total
 
 
 def gradient_buckets(model) -> List[List[torch.nn.Parameter]]:
@@ -206,3 +246,68 @@ def train_step(args, model, optim, nodes_dist, x, h, node_mask, edge_mask, conte
     if ema is not None and model_ema is not None and getattr(args, "ema_decay", 0) > 0:
         ema.update_model_average(model_ema, model)
     return nll.detach(), grad_norm
+
+
+class GraphedTrainStep:
+    """train_step (zero, loss, backward, bucketed all-reduce, adaptive clipping, AdamW, EMA) captured ONCE as a CUDA graph
+    for a fixed batch signature (the molecule sizes, i.e. node_mask / edge_mask) and replayed per step: the ~3000 kernel
+    launches of the eager step cost one graph launch, no host synchronisation happens inside the step (the gradient-norm
+    history lives on the device: DeviceGradClip), and the step's inputs are copied into static buffers.  Batches with
+    another signature need their own instance (or the eager `train_step`).
+
+    The optimiser must have been built with `capturable=True` (get_optim(..., capturable=True))."""
+
+    def __init__(self, args, model, optim, nodes_dist, x, h, node_mask, edge_mask, context, *, model_ema=None,
+                 ema: Optional[EMA] = None, buckets: Optional[FlatGradBuckets] = None, clip: Optional[DeviceGradClip] = None,
+                 warmup: int = 3):
+        dev = x.device
+        self.args, self.model, self.optim, self.nodes_dist = args, model, optim, nodes_dist
+        self.model_ema, self.ema = model_ema, ema
+        self.buckets = buckets if buckets is not None else FlatGradBuckets(model)
+        self.clip = clip if clip is not None else (DeviceGradClip(dev) if getattr(args, "clip_grad", True) else None)
+        self.x = x.clone()
+        self.h = {k: v.clone() for k, v in h.items()}
+        self.context = None if context is None else context.clone()
+        self.node_mask, self.edge_mask = node_mask, edge_mask
+        if float((x * (1 - node_mask)).abs().sum()) >= 1e-8:          # the step itself must not read back (losses.py)
+            raise AssertionError("x is not masked")
+        model.train()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                                  # eager warm-up on a side stream (caches, NCCL, AdamW state)
+            for _ in range(max(1, warmup)):                            # >= 1: mask packing and lazy state need host work
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.nll, self.grad_norm = self._body()
+
+    def _body(self):
+        self.buckets.zero()
+        nll, reg_term, _ = losses.compute_loss_and_nll(self.args, self.model, self.nodes_dist, self.x, self.h,
+                                                       self.node_mask, self.edge_mask, self.context)
+        loss = nll + getattr(self.args, "ode_regularization", 0.0) * reg_term.squeeze()
+        loss.backward()
+        self.buckets.finish()
+        grad_norm = self.clip.clip_(self.buckets.flat) if self.clip is not None else torch.zeros((), device=nll.device)
+        self.optim.step()
+        if self.ema is not None and self.model_ema is not None and getattr(self.args, "ema_decay", 0) > 0:
+            self.ema.update_model_average(self.model_ema, self.model)
+        return nll.detach(), grad_norm
+
+    def __call__(self, x, h=None, context=None):
+        """Copies the step's inputs into the static buffers (asynchronously) and replays the graph.  Returns device
+        scalars (nll, gradient norm) that the next call overwrites."""
+        self.x.copy_(x, non_blocking=True)
+        if h is not None:
+            for k, v in h.items():
+                if v.numel():
+                    self.h[k].copy_(v, non_blocking=True)
+        if context is not None and self.context is not None:
+            self.context.copy_(context, non_blocking=True)
+        self.graph.replay()
+        for m in self.model.modules():                 # weights changed without python noticing: drop packed weight images
+            if hasattr(m, "_pack_key"):
+                m._pack_key = None
+        return self.nll, self.grad_norm
