@@ -52,6 +52,7 @@ _SIGS = {
     "geoldm_last_error": (C.c_char_p, []),
     "geoldm_has_tcgen05": (C.c_int, []),
     "geoldm_batch_tile_meta": (C.c_int, [C.POINTER(Batch), fp, fp]),
+    "geoldm_node_chain": (C.c_int, [C.c_int, fp, fp, C.c_float, fp, fp, fp, fp, fp, fp, C.c_int, fp, fp, fp, C.c_int, fp]),
     "geoldm_egnn_workspace_bytes": (C.c_size_t, [C.POINTER(EgnnConfig), C.c_int, C.c_int]),
     "geoldm_egnn_forward": (C.c_int, [C.POINTER(EgnnConfig), C.POINTER(EgnnWeights), C.POINTER(Batch), fp, fp, fp, fp,
                                       fp, fp, C.c_size_t, fp]),

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace geoldm {
@@ -55,6 +57,12 @@ using namespace geoldm;
 extern "C" {
 
 int geoldm_abi_version(void) { return GEOLDM_ABI_VERSION; }
+int geoldm_node_chain(int H, const float* h, const float* agg, float agg_div, const void* pack1, const float* b1,
+                      const void* pack2, const float* b2, const void* pack3, const float* b3, int n_blocks3, float* h_out,
+                      float* pq_out, float* agg_zero, int m, void* stream) {
+  return geoldm::launch_node_chain16(H, h, agg, agg_div, pack1, b1, pack2, b2, pack3, b3, n_blocks3, h_out, pq_out, agg_zero, m,
+                                     (cudaStream_t)stream);
+}
 const char* geoldm_last_error(void) { return g_err; }
 
 size_t geoldm_egnn_workspace_bytes(const geoldm_egnn_config* cfg, int n_node, int n_edge) {
@@ -111,8 +119,19 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
     GEOLDM_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "egnn_forward: memset failed: %s",
                    cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
+  // fp16-split path, opt-in (GEOLDM_TC_CHAIN=1): node_mlp.0 -> SiLU -> node_mlp.2 -> + h -> the projections that read the
+  // new h as ONE persistent launch per GCL (chain16_kernel: intermediates stay in shared memory as operand images).
+  // Parity-green, but MEASURED SLOWER than the three dense launches at the bench size (105.7 vs 99.9 us per block at
+  // 22 576 rows: 89 tile pairs on 74 CTA pairs make two full rounds of the whole chain, and a tile's phases run
+  // back to back with their epilogue latencies exposed; profiles/README.md), so the dense launches stay the default.
+  static int chain_env = -1;
+  if (chain_env < 0) { const char* e = getenv("GEOLDM_TC_CHAIN"); chain_env = e ? atoi(e) : 0; }
+  const bool chain = chain_env && cfg->mma_mode == GEOLDM_MMA_3XF16;
   for (int l = 0; l < cfg->n_layers; ++l) {
     const geoldm_block& blk = w->block[l];
+    bool pq_ready = false;          // the chain kernel has already produced the projections the next consumer needs
+    bool equiv_pq_ready = false;
+    int equiv_pq_ld = 2 * H;
     if (pre_dist) {
       if (l == 0) r_edge = ws.d0_edge;                    // x == x_in in the first block
       else { if ((rc = launch_edge_dist(*b, x_cur, ws.r_edge, ws.u_edge, cfg->norm_constant, st))) return rc; r_edge = ws.r_edge; }
@@ -123,6 +142,8 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
       int pq_ld = 2 * H;
       if (s == 0 && pq_next) {
         pq = pq_next; pq_ld = pq_next_ld;
+      } else if (pq_ready) {
+        pq_ready = false;             // written into ws.pq by the previous sublayer's chain kernel
       } else if (tcore) {
         if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, g.edge.tc_pack_pq, 2, g.edge.pq_b, nullptr, 0, ws.pq, N, st))) return rc;
       } else {
@@ -133,7 +154,18 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
         GEOLDM_REQUIRE(e == cudaSuccess, "egnn_forward: memset failed: %s", cudaGetErrorString(e));
       }
       if ((rc = edge_dispatch(*cfg, g.edge, *b, false, pq, pq_ld, x_cur, x_in, ws.agg, st, r_edge, d0_edge))) return rc;
-      if (tcore) {
+      if (chain) {
+        const void* pack3; const float* b3; int n_pb;
+        if (s + 1 < cfg->inv_sublayers) {                       // next sublayer's GCL projections
+          pack3 = blk.gcl[s + 1].edge.tc_pack_pq; b3 = blk.gcl[s + 1].edge.pq_b; n_pb = 2; pq_ready = true;
+        } else if (blk.tc_pack_pq4 && l + 1 < cfg->n_layers) {  // this block's coord_mlp + next block's gcl_0
+          pack3 = blk.tc_pack_pq4; b3 = blk.pq4_b; n_pb = 4; equiv_pq_ready = true; equiv_pq_ld = 4 * H;
+        } else {                                                // this block's coord_mlp only
+          pack3 = blk.equiv.tc_pack_pq; b3 = blk.equiv.pq_b; n_pb = 2; equiv_pq_ready = true; equiv_pq_ld = 2 * H;
+        }
+        if ((rc = launch_node_chain16(H, h, ws.agg, cfg->agg_div, g.tc_pack_node1, g.node_b1, g.tc_pack_node2, g.node_b2,
+                                      pack3, b3, n_pb, h2, ws.pq, ws.agg, N, st))) return rc;
+      } else if (tcore) {
         if ((rc = launch_linear_tc(H, terms, h, H, ws.agg, H, cfg->agg_div, g.tc_pack_node1, 1, g.node_b1, nullptr, 1, ws.t1, N, st))) return rc;
         if ((rc = launch_linear_tc(H, terms, ws.t1, H, nullptr, 0, 1.f, g.tc_pack_node2, 1, g.node_b2, h, 2, h2, N, st,
                                    self_clean ? ws.agg : nullptr))) return rc;
@@ -146,7 +178,10 @@ int geoldm_egnn_forward(const geoldm_egnn_config* cfg, const geoldm_egnn_weights
     const geoldm_edge_mlp& e = blk.equiv;
     int pq_ld = 2 * H;
     pq_next = nullptr;
-    if (tcore && blk.tc_pack_pq4 && l + 1 < cfg->n_layers) {
+    if (equiv_pq_ready) {
+      pq_ld = equiv_pq_ld;
+      if (pq_ld == 4 * H) { pq_next = ws.pq + 2 * H; pq_next_ld = 4 * H; }
+    } else if (tcore && blk.tc_pack_pq4 && l + 1 < cfg->n_layers) {
       if ((rc = launch_linear_tc(H, terms, h, H, nullptr, 0, 1.f, blk.tc_pack_pq4, 4, blk.pq4_b, nullptr, 0, ws.pq, N, st))) return rc;
       pq_ld = 4 * H;
       pq_next = ws.pq + 2 * H;

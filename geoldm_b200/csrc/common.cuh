@@ -182,6 +182,10 @@ int launch_edge_dist(const geoldm_batch& b, const float* x, float* out, float* u
 int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, float a2_div, const void* w_pack,
                        int n_blocks, const float* bias, const float* res, int epi, float* out, int m, cudaStream_t st,
                        float* zero_buf = nullptr);   // zero_buf: [m][n_blocks H] buffer cleared by the residual epilogue
+// fused node chain of one GCL + the following first-layer projections (edge_tc16.cu: chain16_kernel)
+int launch_node_chain16(int H, const float* h, const float* agg, float agg_div, const void* pack1, const float* b1,
+                        const void* pack2, const float* b2, const void* pack3, const float* b3, int n_pb, float* h_out,
+                        float* pq_out, float* zero_buf, int m, cudaStream_t st);
 int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,
                          const void* w_pack, float* out, cudaStream_t st);
 int launch_embed(int n_node, int H, int F, const float* h_in, const float* w, const float* b, float* h,

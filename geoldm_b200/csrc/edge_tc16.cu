@@ -1083,6 +1083,481 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
   *reinterpret_cast<__half*>(img + off) = hi;
   *reinterpret_cast<__half*>(img + (size_t)NH * 128 + off) = lo;
 }
+// =====================================================================================================================
+// Fused node chain of one GCL (egnn/egnn_new.py:47-56) plus the first-layer projections that read its output:
+//     t1 = SiLU([h | agg / div] W1^T + b1)         (node_mlp.0, K = 2H)
+//     h' = h + t1 W2^T + b2                        (node_mlp.2 + residual, K = H)
+//     pq = h' Wp^T + bp                            (n_pb column blocks of H: the P|Q projections of the next edge MLPs)
+// ONE persistent launch per GCL instead of three dense launches: a CTA pair keeps a 256-row tile on chip through all three
+// GEMMs.  t1 and h' never exist as fp32 matrices between the GEMMs: the epilogue of a phase writes its result straight into
+// shared memory as the NEXT phase's A operand (fp16 hi | lo images in the canonical SWIZZLE_128B K-major layout, same
+// K order inside a slab as the producers use), so phases 2 and 3 need no producer work, no global round trip and no
+// extra launch.  Phase 1 streams [h | agg] through the usual producer ring, which aliases the first two slabs of the image
+// (the images are written only after the phase-1 MMAs have completed; the producers of the next tile wait for img_free).
+// Accumulator regions alternate per GEMM (phase 1 -> 0, phase 2 -> 1, phase 3 blocks 0,1,0,1), so an epilogue overlaps the
+// MMAs that follow it.  Roles: 8 epilogue warps, 16 producer warps, loader, MMA issuer (832 threads).
+struct ChainArgs {
+  int n_tile, n_rows;
+  const float* h; const float* agg; float agg_div;
+  const uint8_t* pack1; const float* b1;
+  const uint8_t* pack2; const float* b2;
+  const uint8_t* pack3; const float* b3; int n_pb;
+  float* h_out; float* pq_out; float* zero_buf;
+  float rz1, rz2;                 // round-toward-zero compensation for K = 2H and K = H
+};
+
+template <int H>
+struct ChainSmem {
+  static constexpr int KS = H / BK;
+  static constexpr int NWS = 2, NAS = 2;
+  static constexpr int IMG_SLABS = KS > NAS ? KS : NAS;
+  static constexpr uint32_t NH = H / 2;
+  static constexpr uint32_t W_IMG = NH * 128u;
+  static constexpr uint32_t W_STAGE = 2u * W_IMG;
+  static constexpr uint32_t A_SLAB = 2u * TM * 128u;
+  static constexpr uint32_t OFF_W = 0;
+  static constexpr uint32_t OFF_A = OFF_W + NWS * W_STAGE;           // producer ring = image slabs 0, 1
+  static constexpr uint32_t OFF_T = OFF_A + IMG_SLABS * A_SLAB;       // 8 warp-private [32][20] fp32 transposition tiles
+  static constexpr uint32_t OFF_BAR = OFF_T + 8u * 32 * 20 * 4;
+  static constexpr int N_BAR = 3 * NWS + 2 * NAS + 4 + KS + 1;
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + N_BAR * 8;
+  static constexpr uint32_t BYTES = OFF_TMEM + 16;
+  static constexpr uint32_t ALLOC = BYTES + 1024;
+};
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+#ifndef GEOLDM_CHAIN_PROD_W
+#define GEOLDM_CHAIN_PROD_W 16
+#endif
+constexpr int CHAIN_THREADS = 32 * (8 + GEOLDM_CHAIN_PROD_W + 2);
+template <int H>
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain16_kernel(const ChainArgs a) {
+  using S = ChainSmem<H>;
+  constexpr int KS = S::KS, NWS = S::NWS, NAS = S::NAS;
+  constexpr int EPI_W = 8, PROD_W = GEOLDM_CHAIN_PROD_W, EPI_T = 32 * EPI_W, WARP_LOAD = EPI_W + PROD_W, WARP_MMA = WARP_LOAD + 1;
+  constexpr int ROWS_PT = 128 / (4 * PROD_W);     // 2 (16 producer warps) or 4 (8)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + NWS;
+  uint64_t* w_peer = bars + 2 * NWS;
+  uint64_t* a_full = bars + 3 * NWS;
+  uint64_t* a_empty = a_full + NAS;
+  uint64_t* acc_full = a_empty + NAS;      // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* img_full = acc_empty + 2;      // [KS] slab s of the operand image is complete in BOTH CTAs
+  uint64_t* img_free = img_full + KS;      // [1] every MMA of the tile has completed: ring / image may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  constexpr uint16_t cmask = 3;
+  const int n_pairs = (a.n_tile + 1) / 2;
+  const int n_workers = (int)gridDim.x / 2;
+  const int worker = (int)blockIdx.x / 2;
+  const int n_iter = worker < n_pairs ? (n_pairs - worker + n_workers - 1) / n_workers : 0;   // same for both CTAs of a pair
+
+  if (tid == 0) {
+    for (int s = 0; s < NWS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&w_peer[s], 1); }
+    for (int s = 0; s < NAS; ++s) { mbar_init(&a_full[s], 2 * PROD_W); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * EPI_W); }
+    for (int s = 0; s < KS; ++s) mbar_init(&img_full[s], 2 * EPI_W);       // (4 lane quarters x 2 column pieces) x 2 CTAs
+    mbar_init(img_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+  pdl_launch_dependents();
+  pdl_wait_prior();
+
+  auto tile_of = [&](int iter, int& row0, int& nrows) {
+    const int tile = 2 * (iter * n_workers + worker) + (int)crank;
+    row0 = tile * TM;
+    nrows = tile < a.n_tile ? min(TM, a.n_rows - row0) : 0;
+    if (nrows <= 0) { row0 = 0; nrows = 0; }
+  };
+  const int stages_per_iter = (3 + a.n_pb) * KS;
+
+  if (warp == WARP_LOAD) {
+    if (lane == 0) {
+      uint32_t wit = 0;
+      for (int iter = 0; iter < n_iter; ++iter)
+        for (int ph = 0; ph < 3; ++ph) {
+          const uint8_t* pack = (ph == 0 ? a.pack1 : ph == 1 ? a.pack2 : a.pack3) + PACK_HDR;
+          const int nb = ph == 2 ? a.n_pb : 1, ns = ph == 0 ? 2 * KS : KS;
+          for (int bs = 0; bs < nb * ns; ++bs, ++wit) {
+            const int st = wit % NWS;
+            mbar_wait(&w_empty[st], ((wit / NWS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&w_full[st], S::W_STAGE);
+            bulk_g2s(smem + S::OFF_W + st * S::W_STAGE, pack + (size_t)(2 * bs + crank) * S::W_STAGE, S::W_STAGE, &w_full[st]);
+          }
+        }
+    } else if (lane == 1 && crank == 1) {
+      uint32_t wit = 0;
+      for (int iter = 0; iter < n_iter; ++iter)
+        for (int s = 0; s < stages_per_iter; ++s, ++wit) {
+          const int st = wit % NWS;
+          mbar_wait(&w_full[st], (wit / NWS) & 1);
+          mbar_arrive_remote(&w_peer[st], 0);
+        }
+    }
+  } else if (warp == WARP_MMA) {
+    if (crank == 0) {
+      const uint32_t idesc = make_idesc_f16_m256(H);
+      uint32_t wit = 0, ait = 0, acc_it = 0, img_gen = 0;
+      // one k-slab: A images at a_hi (lo image TM * 128 bytes behind), W stage wst
+      TC_PROF(long long t_acc = 0; long long t_a = 0; long long t_w = 0; long long t_i2 = 0; long long t_i3 = 0; long long t_p1 = 0;
+              long long t_p2 = 0; long long t_p3 = 0; const long long t_begin = clock64();)
+      auto slab = [&](uint32_t a_hi, int wst, bool first, uint32_t d_tmem) {
+        TC_PROF(const long long tw0 = clock64();)
+        mbar_wait(&w_full[wst], (wit / NWS) & 1);
+        mbar_wait_cluster(&w_peer[wst], (wit / NWS) & 1);
+        TC_PROF(t_w += clock64() - tw0;)
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_lo = a_hi + TM * 128;
+          const uint32_t w_hi = smem_u32(smem + S::OFF_W + wst * S::W_STAGE);
+          const uint32_t w_lo = w_hi + S::W_IMG;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da_hi = make_smem_desc_sw128(a_hi + kk * 32), da_lo = make_smem_desc_sw128(a_lo + kk * 32);
+            const uint64_t dw_hi = make_smem_desc_sw128(w_hi + kk * 32), dw_lo = make_smem_desc_sw128(w_lo + kk * 32);
+            mma_f16_pair(d_tmem, da_lo, dw_hi, idesc, !(first && kk == 0));
+            mma_f16_pair(d_tmem, da_hi, dw_lo, idesc, 1);
+            mma_f16_pair(d_tmem, da_hi, dw_hi, idesc, 1);
+          }
+          mma_commit_pair(&w_empty[wst], cmask);
+        }
+      };
+      for (int iter = 0; iter < n_iter; ++iter) {
+        // ---- phase 1: [h | agg] from the producer ring ----------------------------------------------------------------
+        TC_PROF(const long long tp1 = clock64();)
+        {
+          const int region = acc_it & 1;
+          TC_PROF(const long long ta0 = clock64();)
+          mbar_wait_cluster(&acc_empty[region], ((acc_it >> 1) & 1) ^ 1);
+          TC_PROF(t_acc += clock64() - ta0;)
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + region * 256;
+          for (int s = 0; s < 2 * KS; ++s, ++ait, ++wit) {
+            const int ast = ait % NAS;
+            TC_PROF(const long long tf0 = clock64();)
+            mbar_wait_cluster(&a_full[ast], (ait / NAS) & 1);
+            TC_PROF(t_a += clock64() - tf0;)
+            slab(sbase + S::OFF_A + ast * S::A_SLAB, wit % NWS, s == 0, d_tmem);
+            if (lane == 0) {
+              mma_commit_pair(&a_empty[ast], cmask);
+              if (s == 2 * KS - 1) mma_commit_pair(&acc_full[region], cmask);
+            }
+            __syncwarp();
+          }
+          ++acc_it;
+        }
+        // ---- phase 2 (A = t1 image) and phase 3 (A = h' image, n_pb column blocks) ---------------------------------------
+        TC_PROF(t_p1 += clock64() - tp1;)
+        for (int ph = 1; ph < 3; ++ph) {
+          TC_PROF(const long long tph = clock64();)
+          const int nb = ph == 2 ? a.n_pb : 1;
+          for (int blk = 0; blk < nb; ++blk) {
+            const int region = acc_it & 1;
+            TC_PROF(const long long ta0 = clock64();)
+            mbar_wait_cluster(&acc_empty[region], ((acc_it >> 1) & 1) ^ 1);
+            TC_PROF(t_acc += clock64() - ta0;)
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + region * 256;
+            for (int s = 0; s < KS; ++s, ++wit) {
+              TC_PROF(const long long ti0 = clock64();)
+              if (blk == 0) mbar_wait_cluster(&img_full[s], img_gen & 1);
+              TC_PROF(if (ph == 1) t_i2 += clock64() - ti0; else t_i3 += clock64() - ti0;)
+              slab(sbase + S::OFF_A + s * S::A_SLAB, wit % NWS, s == 0, d_tmem);
+              if (lane == 0 && s == KS - 1) mma_commit_pair(&acc_full[region], cmask);
+              __syncwarp();
+            }
+            ++acc_it;
+          }
+          ++img_gen;
+          TC_PROF(if (ph == 1) t_p2 += clock64() - tph; else t_p3 += clock64() - tph;)
+        }
+        if (lane == 0) mma_commit_pair(img_free, cmask);
+        __syncwarp();
+      }
+      TC_PROF(if (lane == 0 && blockIdx.x == 0) {
+        g_tc16_stats[0] += (unsigned long long)(clock64() - t_begin); g_tc16_stats[1] += (unsigned long long)t_acc;
+        g_tc16_stats[2] += (unsigned long long)t_a; g_tc16_stats[3] += (unsigned long long)t_w; g_tc16_stats[4] += 1ull;
+        g_tc16_stats[5] += (unsigned long long)n_iter; g_tc16_stats[6] += (unsigned long long)t_i2;
+        g_tc16_stats[7] += (unsigned long long)t_i3; g_tc16_stats[8] += (unsigned long long)t_p1;
+        g_tc16_stats[9] += (unsigned long long)t_p2; g_tc16_stats[10] += (unsigned long long)t_p3;
+      })
+    }
+  } else if (warp >= EPI_W) {
+    // =========================== producers: [h | agg / div] -> fp16 hi | lo slabs ======================================
+    const int pt = tid - EPI_T;
+    const int chunk = pt & 7;
+    const int rg = pt >> 3;
+    uint32_t it = 0;
+    for (int iter = 0; iter < n_iter; ++iter) {
+      int row0, nrows;
+      tile_of(iter, row0, nrows);
+      const int rlast = nrows > 0 ? nrows - 1 : 0;
+      const float* ph_[ROWS_PT];
+      const float* pa_[ROWS_PT];
+#pragma unroll
+      for (int p = 0; p < ROWS_PT; ++p) {
+        const size_t grow = (size_t)(row0 + min(rg * ROWS_PT + p, rlast));
+        ph_[p] = a.h + grow * H + 4 * chunk;
+        pa_[p] = a.agg + grow * H + 4 * chunk;
+      }
+      if (iter > 0) mbar_wait(img_free, (iter - 1) & 1);        // the ring aliases the image the previous tile's MMAs read
+#pragma unroll 1
+      for (int s = 0; s < 2 * KS; ++s, ++it) {
+        const int st = it % NAS;
+        const bool from_h = s < KS;
+        const int k0 = (from_h ? s : s - KS) * BK;
+        float4 v[ROWS_PT][2];
+#pragma unroll
+        for (int p = 0; p < ROWS_PT; ++p) {
+          const float* src = (from_h ? ph_[p] : pa_[p]) + k0;
+          v[p][0] = __ldg(reinterpret_cast<const float4*>(src));
+          v[p][1] = __ldg(reinterpret_cast<const float4*>(src + KH));
+        }
+        mbar_wait(&a_empty[st], ((it / NAS) & 1) ^ 1);
+        const uint32_t a_hi = sbase + S::OFF_A + st * S::A_SLAB;
+#pragma unroll
+        for (int p = 0; p < ROWS_PT; ++p) {
+          float e[8] = {v[p][0].x, v[p][0].y, v[p][0].z, v[p][0].w, v[p][1].x, v[p][1].y, v[p][1].z, v[p][1].w};
+          if (!from_h && a.agg_div != 1.0f) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) e[c] = __fdiv_rn(e[c], a.agg_div);
+          }
+          uint4 hi, lo;
+          split_f16x8(e, hi, lo);
+          const uint32_t off = sw128_off(rg * ROWS_PT + p, chunk);
+          sts128(a_hi + off, hi);
+          sts128(a_hi + TM * 128 + off, lo);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { if (crank != 0) mbar_arrive_remote(&a_full[st], 0); else mbar_arrive(&a_full[st]); }
+      }
+    }
+  } else {
+    // =========================== epilogue: thread = (row = TMEM lane, column half) ======================================
+    const int r = (warp & 3) * 32 + lane;
+    const int hf = warp >> 2;
+    constexpr int HC = H / 2;
+    constexpr int NCH = HC / 32;
+    const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * HC;
+    const float scale1 = __ldg(reinterpret_cast<const float*>(a.pack1)) * a.rz1;
+    const float scale2 = __ldg(reinterpret_cast<const float*>(a.pack2)) * a.rz2;
+    const float scale3 = __ldg(reinterpret_cast<const float*>(a.pack3)) * a.rz2;
+    const int ld_pq = a.n_pb * H;
+    uint32_t acc_it = 0;
+    auto release_acc = [&](int region) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (crank != 0) mbar_arrive_remote(&acc_empty[region], 0); else mbar_arrive(&acc_empty[region]); }
+    };
+    // four consecutive values of this row (slab columns 4c..4c+3 of a 32-column piece) -> the fp16 hi | lo halves of the
+    // operand image: the 16-byte chunk c of a slab row holds slab columns 4c..4c+3 (low 8 bytes) and 32+4c..32+4c+3 (high)
+    auto put4 = [&](uint32_t img_piece, int c, f32x2 m0, f32x2 m1) {
+      uint32_t h0, l0, h1, l1;
+      split_f16x2(m0, h0, l0);
+      split_f16x2(m1, h1, l1);
+      const uint32_t off = img_piece + sw128_off(r, c);
+      sts64(off, h0, h1);
+      sts64(off + TM * 128, l0, l1);
+    };
+    auto piece_done = [&](int sl) {                // this warp's 32 rows x 32 columns of image slab sl are in place
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { if (crank != 0) mbar_arrive_remote(&img_full[sl], 0); else mbar_arrive(&img_full[sl]); }
+    };
+    for (int iter = 0; iter < n_iter; ++iter) {
+      int row0, nrows;
+      tile_of(iter, row0, nrows);
+      const bool valid = r < nrows;
+      const size_t grow = (size_t)(row0 + (valid ? r : 0));
+      // ---- epilogue 1: t1 = SiLU(scale D + b1) -> image ------------------------------------------------------------------
+      {
+        const int region = acc_it & 1;
+        mbar_wait(&acc_full[region], (acc_it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tlane + region * 256;
+#pragma unroll 1
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cc * 32, v);
+          tmem_ld_wait();
+          if (cc == NCH - 1) release_acc(region);
+          const int col0 = hf * HC + cc * 32;
+          const uint32_t img_piece = sbase + S::OFF_A + (col0 / BK) * S::A_SLAB + ((col0 / 32) & 1) * 8;
+          const f32x2 sc = pk2(scale1, scale1);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + col0 + 4 * c4));
+            f32x2 m0 = fma2(pk2(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1])), sc, pk2(b4.x, b4.y));
+            f32x2 m1 = fma2(pk2(__uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3])), sc, pk2(b4.z, b4.w));
+            silu_x4(m0, m1);
+            put4(img_piece, c4, m0, m1);
+          }
+          piece_done(col0 / BK);
+        }
+        ++acc_it;
+      }
+      // Global rows move COALESCED: every 32 x 16 piece of the accumulator goes through this warp's transposition tile and is
+      // then handled by lane (rl = row % 8, c4 = 16-byte column group): 8 rows x 64 contiguous bytes per instruction.
+      const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 20 * 4);
+      const int rl = lane >> 2, c4l = lane & 3;
+      const int wrow0 = row0 + (warp & 3) * 32;
+      const int nval = min(32, nrows - (warp & 3) * 32);        // rows of this warp that exist (may be <= 0)
+      auto to_tile = [&](const uint32_t (&v)[16]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128f(Tw + (lane * 20 + 4 * q) * 4, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                             __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+      };
+      // ---- epilogue 2: h' = scale D + b2 + h -> global (fp32) and image; the consumed agg rows are handed back zeroed ----
+      {
+        const int region = acc_it & 1;
+        mbar_wait(&acc_full[region], (acc_it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tlane + region * 256;
+#pragma unroll 1
+        for (int sc = 0; sc < HC / 16; ++sc) {
+          uint32_t v[16];
+          tmem_ld16(taddr + sc * 16, v);
+          const int col = hf * HC + sc * 16 + 4 * c4l;            // this lane's 4 columns in the coalesced phase
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b2 + col));
+          float4 rs[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int grow_c = min(wrow0 + max(0, min(8 * k + rl, nval - 1)), a.n_rows - 1);      // clamped: in bounds
+            rs[k] = __ldg(reinterpret_cast<const float4*>(a.h + (size_t)grow_c * H + col));
+          }
+          tmem_ld_wait();
+          if (sc == HC / 16 - 1) release_acc(region);
+          to_tile(v);
+          __syncwarp();
+          const int lc = col % BK;                                 // column inside its k-slab
+          const uint32_t img_piece = sbase + S::OFF_A + (col / BK) * S::A_SLAB + (lc / 32) * 8;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = 8 * k + rl;
+            const float4 t = lds128f(Tw + (row * 20 + 4 * c4l) * 4);
+            const float o0 = fmaf(t.x, scale2, b4.x) + rs[k].x, o1 = fmaf(t.y, scale2, b4.y) + rs[k].y;
+            const float o2 = fmaf(t.z, scale2, b4.z) + rs[k].z, o3 = fmaf(t.w, scale2, b4.w) + rs[k].w;
+            if (row < nval) {
+              const size_t goff = (size_t)(wrow0 + row) * H + col;
+              *reinterpret_cast<float4*>(a.h_out + goff) = make_float4(o0, o1, o2, o3);
+              if (a.zero_buf) *reinterpret_cast<float4*>(a.zero_buf + goff) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint32_t h0, l0, h1, l1;
+            split_f16x2(pk2(o0, o1), h0, l0);
+            split_f16x2(pk2(o2, o3), h1, l1);
+            const uint32_t off = img_piece + sw128_off((warp & 3) * 32 + row, (lc % 32) / 4);
+            sts64(off, h0, h1);
+            sts64(off + TM * 128, l0, l1);
+          }
+          if (sc & 1) piece_done((hf * HC + sc * 16) / BK);          // 32 columns of image slab complete for this warp's rows
+          else __syncwarp();
+        }
+        ++acc_it;
+      }
+      // ---- epilogue 3: pq block = scale D + b3 -> global ---------------------------------------------------------------------
+      for (int blk = 0; blk < a.n_pb; ++blk) {
+        const int region = acc_it & 1;
+        mbar_wait(&acc_full[region], (acc_it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tlane + region * 256;
+#pragma unroll 1
+        for (int sc = 0; sc < HC / 16; ++sc) {
+          uint32_t v[16];
+          tmem_ld16(taddr + sc * 16, v);
+          const int col = blk * H + hf * HC + sc * 16 + 4 * c4l;
+          const float4 b4 = a.b3 ? __ldg(reinterpret_cast<const float4*>(a.b3 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+          if (sc == HC / 16 - 1) release_acc(region);
+          to_tile(v);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = 8 * k + rl;
+            const float4 t = lds128f(Tw + (row * 20 + 4 * c4l) * 4);
+            if (row < nval)
+              *reinterpret_cast<float4*>(a.pq_out + (size_t)(wrow0 + row) * ld_pq + col) =
+                  make_float4(fmaf(t.x, scale3, b4.x), fmaf(t.y, scale3, b4.y), fmaf(t.z, scale3, b4.z), fmaf(t.w, scale3, b4.w));
+          }
+          __syncwarp();
+        }
+        ++acc_it;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+template <int H>
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
+  using S = ChainSmem<H>;
+  static int sm_count = 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chain16_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
+    if (e != cudaSuccess) {
+      set_error("chain16_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
+      return -2;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  if (a.n_tile == 0) return 0;
+  const int work = (a.n_tile + 1) / 2 * 2;
+  int grid = work < sm_count ? work : sm_count;
+  grid = grid / 2 * 2;
+  ChainArgs args = a;
+  args.rz1 = 1.0f + RZ_BIAS_PER_MMA * (float)(2 * S::KS * (BK / 16) * 3);
+  args.rz2 = 1.0f + RZ_BIAS_PER_MMA * (float)(S::KS * (BK / 16) * 3);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CHAIN_THREADS);
+  cfg.dynamicSmemBytes = S::ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, chain16_kernel<H>, args);
+  if (e != cudaSuccess) {
+    set_error("chain16_kernel launch: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
 // One warp per tile: {first receiver, first sender, staged, 0}.  Edge rows are sorted by (molecule, receiver, sender), so the
 // first / last row hold the extreme receivers; senders are scanned.
 __global__ void tile_meta_kernel(int n_tile, int tile_m, int n_edge, const int* __restrict__ tile_row,
@@ -1154,6 +1629,28 @@ int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, 
   a.w_pack = reinterpret_cast<const uint8_t*>(w_pack);
   a.b2 = bias; a.res = res; a.epi = epi; a.out = out; a.ldo = n_blocks * H; a.zero_buf = zero_buf;
   return launch_h<MODE_DENSE>(H, a, st);
+}
+
+int launch_node_chain16(int H, const float* h, const float* agg, float agg_div, const void* pack1, const float* b1,
+                        const void* pack2, const float* b2, const void* pack3, const float* b3, int n_pb, float* h_out,
+                        float* pq_out, float* zero_buf, int m, cudaStream_t st) {
+  GEOLDM_REQUIRE(pack1 && pack2 && pack3 && b1 && b2, "node_chain16: weight packs / biases missing");
+  GEOLDM_REQUIRE(n_pb >= 1 && n_pb <= 8, "node_chain16: %d projection blocks", n_pb);
+  GEOLDM_REQUIRE(h != h_out, "node_chain16: h_out must not alias h (rows are re-read as the residual)");
+  ChainArgs a{};
+  a.n_tile = (m + TM - 1) / TM; a.n_rows = m;
+  a.h = h; a.agg = agg; a.agg_div = agg_div;
+  a.pack1 = reinterpret_cast<const uint8_t*>(pack1); a.b1 = b1;
+  a.pack2 = reinterpret_cast<const uint8_t*>(pack2); a.b2 = b2;
+  a.pack3 = reinterpret_cast<const uint8_t*>(pack3); a.b3 = b3; a.n_pb = n_pb;
+  a.h_out = h_out; a.pq_out = pq_out; a.zero_buf = zero_buf;
+  switch (H) {
+    case 64: return launch_chain<64>(a, st);
+    case 128: return launch_chain<128>(a, st);
+    case 192: return launch_chain<192>(a, st);
+    case 256: return launch_chain<256>(a, st);
+    default: set_error("node_chain16 supports hidden_nf 64/128/192/256, got %d", H); return -1;
+  }
 }
 
 int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,

@@ -201,6 +201,16 @@ int geoldm_tc_pack(int H, const float* w, int n_out, int k, void* pack, void* st
  * [2^13, 2^14)), same SWIZZLE_128B K-major order.  H and k multiples of 64. */
 size_t geoldm_tc_pack16_bytes(int H, int n_out, int k);
 int geoldm_tc_pack16(int H, const float* w, int n_out, int k, void* pack, void* stream);
+/* Fused node chain of one GCL (egnn/egnn_new.py:47-56) plus the first-layer projections reading its output, fp16-split
+ * tcgen05 arithmetic, ONE persistent launch (ABI v4):
+ *   t1 = SiLU([h | agg / agg_div] W1^T + b1);  h_out = h + t1 W2^T + b2;  pq_out[:, blk H ..] = h_out Wp_blk^T + b3
+ * pack1 / pack2 / pack3: geoldm_tc_pack16 images of node_mlp.0 (n_out H, k 2H), node_mlp.2 (H, H) and of n_blocks3 stacked
+ * [H][H] projection blocks; pq_out is [m][n_blocks3 H]; agg_zero (may be NULL) = an [m][H] buffer to clear (the consumed
+ * agg); h_out must not alias h.  H in {64,128,192,256}. */
+int geoldm_node_chain(int H, const float* h, const float* agg, float agg_div, const void* pack1, const float* b1,
+                      const void* pack2, const float* b2, const void* pack3, const float* b3, int n_blocks3, float* h_out,
+                      float* pq_out, float* agg_zero, int m, void* stream);
+
 /* same contract as geoldm_linear with n = n_blocks*H outputs, on the tensor cores; terms: 3 = 3xTF32, 1 = TF32,
  * 16 = 3xF16 (w_pack from geoldm_tc_pack16) */
 int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,

@@ -5,6 +5,8 @@ Gate (north_star): fp32 single forward <= 1e-5.  Noise floor of the reference it
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -198,6 +200,62 @@ def test_linear_tc_kernel(dev, m, k1, k2, nb, epi, H, terms):
     err = O.err_metric(out.cpu().double(), ref)
     print(f"[linear_tc] terms={terms} m={m} k={k1}+{k2} n={n} epi={epi}: err {err:.2e}")
     assert err < 5e-6
+
+
+@pytest.mark.parametrize("H,m,nb", [(256, 1154, 4), (64, 333, 2), (192, 700, 2), (128, 129, 4), (256, 22576, 4), (256, 5, 2)])
+def test_node_chain_kernel(dev, H, m, nb):
+    """geoldm_node_chain (node_mlp.0 -> SiLU -> node_mlp.2 -> + h -> nb projection blocks, ONE launch, intermediates as
+    shared-memory operand images) against the float64 expression of egnn_new.py:47-56 and the following nn.Linear."""
+    if not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    from geoldm_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    h = torch.randn(m, H, generator=g)
+    agg = torch.randn(m, H, generator=g) * 3
+    div = 100.0
+    w1 = torch.randn(H, 2 * H, generator=g) / np.sqrt(2 * H)
+    b1 = torch.randn(H, generator=g) * 0.3
+    w2 = torch.randn(H, H, generator=g) / np.sqrt(H)
+    b2 = torch.randn(H, generator=g) * 0.3
+    w3 = torch.randn(nb * H, H, generator=g) / np.sqrt(H)
+    b3 = torch.randn(nb * H, generator=g) * 0.3
+    t1 = torch.nn.functional.silu(torch.cat([h, agg / div], 1).double() @ w1.double().T + b1.double())
+    h_ref = h.double() + t1 @ w2.double().T + b2.double()
+    pq_ref = h_ref @ w3.double().T + b3.double()
+    d = lambda t: t.to(dev).contiguous()
+    Hd, Ad, W1, B1, W2, B2, W3, B3 = map(d, (h, agg, w1, b1, w2, b2, w3, b3))
+    p1 = _tc_pack(L, _lib, 16, H, W1, H, 2 * H, dev)
+    p2 = _tc_pack(L, _lib, 16, H, W2, H, H, dev)
+    p3 = _tc_pack(L, _lib, 16, H, W3, nb * H, H, dev)
+    h_out = torch.full((m, H), float("nan"), device=dev)
+    pq_out = torch.full((m, nb * H), float("nan"), device=dev)
+    agg_in = Ad.clone()
+    _lib.check(L.geoldm_node_chain(H, _lib.ptr(Hd), _lib.ptr(agg_in), div, _lib.ptr(p1), _lib.ptr(B1), _lib.ptr(p2), _lib.ptr(B2),
+                                   _lib.ptr(p3), _lib.ptr(B3), nb, _lib.ptr(h_out), _lib.ptr(pq_out), _lib.ptr(agg_in), m, None),
+               "node_chain")
+    torch.cuda.synchronize()
+    eh = O.err_metric(h_out.cpu().double(), h_ref)
+    ep = O.err_metric(pq_out.cpu().double(), pq_ref)
+    print(f"[node_chain] H={H} m={m} nb={nb}: h' err {eh:.2e}, pq err {ep:.2e}")
+    assert eh < 3e-6 and ep < 5e-6
+    assert float(agg_in.abs().max()) == 0.0          # the consumed agg buffer is handed back zeroed
+    assert torch.equal(Hd.cpu(), h)                  # inputs untouched
+
+
+def test_forward_with_fused_node_chain_subprocess(dev):
+    """The opt-in fused node chain inside the whole forward (GEOLDM_TC_CHAIN=1 is read once per process): the QM9 / GEOM /
+    flag-variant forward goldens in the default arithmetic, in a child process with the switch set."""
+    import subprocess, sys
+    if not _has_tc():
+        pytest.skip("tcgen05 kernels not built")
+    env = dict(os.environ, GEOLDM_TC_CHAIN="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
+                        "(qm9_forward_golden or geom_forward_golden or flag_variants_golden) and 3xf16"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    tail = (r.stdout + r.stderr)[-600:]
+    assert r.returncode == 0 and " passed" in r.stdout, tail
 
 
 @pytest.mark.parametrize("H,nodes", [(256, [29, 3, 17, 18, 5]), (64, [9, 2, 1, 30]), (192, [12, 25]), (32, [70, 4])])
