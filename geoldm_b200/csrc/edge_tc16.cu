@@ -720,33 +720,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
         // (packed fp32 pairs, one reciprocal shared by two values, two partial dots)
         f32x2 dot2 = pk2(0.f, 0.f);
         const f32x2 scale2 = pk2(scale, scale);
-#pragma unroll 1
-        for (int cc = 0; cc < NCH; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(taddr + cc * 32, v);
-          tmem_ld_wait();
-#ifdef GEOLDM_SILU_QUAD
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const float4 b4 = lds128f(s_b2 + (cc * 32 + c8 * 8) * 4), b5 = lds128f(s_b2 + (cc * 32 + c8 * 8 + 4) * 4);
-            const float4 w4 = lds128f(s_wo + (cc * 32 + c8 * 8) * 4), w5 = lds128f(s_wo + (cc * 32 + c8 * 8 + 4) * 4);
-            f32x2 m0 = fma2(pk2(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1])), scale2, pk2(b4.x, b4.y));
-            f32x2 m1 = fma2(pk2(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3])), scale2, pk2(b4.z, b4.w));
-            f32x2 m2 = fma2(pk2(__uint_as_float(v[c8 * 8 + 4]), __uint_as_float(v[c8 * 8 + 5])), scale2, pk2(b5.x, b5.y));
-            f32x2 m3 = fma2(pk2(__uint_as_float(v[c8 * 8 + 6]), __uint_as_float(v[c8 * 8 + 7])), scale2, pk2(b5.z, b5.w));
-            silu_x8(m0, m1, m2, m3);
-            dot2 = fma2(pk2(w4.x, w4.y), m0, dot2);
-            dot2 = fma2(pk2(w4.z, w4.w), m1, dot2);
-            dot2 = fma2(pk2(w5.x, w5.y), m2, dot2);
-            dot2 = fma2(pk2(w5.z, w5.w), m3, dot2);
-            float f0, f1, f2, f3, f4, f5, f6, f7;
-            upk2(m0, f0, f1); upk2(m1, f2, f3); upk2(m2, f4, f5); upk2(m3, f6, f7);
-            v[c8 * 8 + 0] = __float_as_uint(f0); v[c8 * 8 + 1] = __float_as_uint(f1);
-            v[c8 * 8 + 2] = __float_as_uint(f2); v[c8 * 8 + 3] = __float_as_uint(f3);
-            v[c8 * 8 + 4] = __float_as_uint(f4); v[c8 * 8 + 5] = __float_as_uint(f5);
-            v[c8 * 8 + 6] = __float_as_uint(f6); v[c8 * 8 + 7] = __float_as_uint(f7);
-          }
-#else
+        // one 32-column chunk: bias, SiLU, partial dot; the SiLU values go back into v (GCL writes them to TMEM for pass 2)
+        auto p1_chunk = [&](uint32_t (&v)[32], int cc) {
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 b4 = lds128f(s_b2 + (cc * 32 + c4 * 4) * 4);
@@ -762,8 +737,32 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
             v[c4 * 4 + 0] = __float_as_uint(f0); v[c4 * 4 + 1] = __float_as_uint(f1);
             v[c4 * 4 + 2] = __float_as_uint(f2); v[c4 * 4 + 3] = __float_as_uint(f3);
           }
-#endif
           if (MODE == MODE_GCL) tmem_st32(taddr + cc * 32, v);
+        };
+#ifndef GEOLDM_P1_PIPE
+#define GEOLDM_P1_PIPE 1
+#endif
+        if constexpr (GEOLDM_P1_PIPE && NCH % 2 == 0 && MODE == MODE_GCL) {
+          // two register buffers: the TMEM load of chunk cc + 1 is in flight while chunk cc is processed
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr, va);
+#pragma unroll
+          for (int cc = 0; cc < NCH; cc += 2) {
+            tmem_ld_wait();
+            tmem_ld32(taddr + (cc + 1) * 32, vb);
+            p1_chunk(va, cc);
+            tmem_ld_wait();
+            if (cc + 2 < NCH) tmem_ld32(taddr + (cc + 2) * 32, va);
+            p1_chunk(vb, cc + 1);
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc < NCH; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(taddr + cc * 32, v);
+            tmem_ld_wait();
+            p1_chunk(v, cc);
+          }
         }
         float dot;
         {
@@ -848,16 +847,21 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
             float* const out_hi = a.out + (size_t)(recv_hi < 0 ? 0 : recv_hi) * H + hf * HC + 4 * c4;
             const uint32_t tp = Tw + ((8 * grp) * 36 + 4 * c4) * 4;
             const uint32_t tv = Tw + (lane * 36 + 32) * 4;                 // pad columns of row `lane`: carry exchange
+            // the gate is applied inside the sums (fma with the row's gate) instead of on every element before the
+            // transposition: the 8 gates of this lane's row group, through a warp-private shared-memory array
+            const uint32_t s_g = sbase + S::OFF_PS + warp * (32 * 4);
+            sts32f(s_g + 4 * lane, g);
+            __syncwarp();
+            const float4 ga = lds128f(s_g + 32 * grp), gb = lds128f(s_g + 32 * grp + 16);
+            const f32x2 gq[8] = {pk2(ga.x, ga.x), pk2(ga.y, ga.y), pk2(ga.z, ga.z), pk2(ga.w, ga.w),
+                                 pk2(gb.x, gb.x), pk2(gb.y, gb.y), pk2(gb.z, gb.z), pk2(gb.w, gb.w)};
 #pragma unroll 1
             for (int cc = 0; cc < NCH; ++cc) {
               tmem_ld_wait();
               if (cc == NCH - 1) { tc_fence_before(); release_acc(region); }
 #pragma unroll
-              for (int c4i = 0; c4i < 8; ++c4i) {
-                const f32x2 e01 = mul2(pk2(__uint_as_float(v[c4i * 4]), __uint_as_float(v[c4i * 4 + 1])), g2);
-                const f32x2 e23 = mul2(pk2(__uint_as_float(v[c4i * 4 + 2]), __uint_as_float(v[c4i * 4 + 3])), g2);
-                sts128p(Tw + (lane * 36 + c4i * 4) * 4, e01, e23);
-              }
+              for (int c4i = 0; c4i < 8; ++c4i)
+                sts128(Tw + (lane * 36 + c4i * 4) * 4, make_uint4(v[c4i * 4], v[c4i * 4 + 1], v[c4i * 4 + 2], v[c4i * 4 + 3]));
               if (cc + 1 < NCH) tmem_ld32(taddr + (cc + 1) * 32, v);   // in flight while the rows of this chunk are summed
               __syncwarp();
               f32x2 lo0 = pk2(0.f, 0.f), lo1 = lo0, hi0 = lo0, hi1 = lo0;
@@ -865,8 +869,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               for (int q = 0; q < 8; ++q) {
                 f32x2 t0, t1;
                 lds128p(tp + q * (36 * 4), t0, t1);
-                if (q < b) { lo0 = add2(lo0, t0); lo1 = add2(lo1, t1); }
-                else { hi0 = add2(hi0, t0); hi1 = add2(hi1, t1); }
+                if (q < b) { lo0 = fma2(gq[q], t0, lo0); lo1 = fma2(gq[q], t1, lo1); }
+                else { hi0 = fma2(gq[q], t0, hi0); hi1 = fma2(gq[q], t1, hi1); }
               }
               // the segment still open at the end of the group, offered to the following groups
               sts128p(tv, has_inner ? hi0 : lo0, has_inner ? hi1 : lo1);
