@@ -423,6 +423,9 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
+    last_nll = float(nll)
+    step.close()                                               # the graph holds NCCL work: release it before the process group goes
+    nll = torch.tensor(last_nll)
     return {"workload": "BASELINE.json configs[4]: conditional QM9 GeoLDM training step, nf=192 n_layers=9, 64 molecules "
                         "per GPU, trainable first stage, AdamW + EMA, gradient all-reduce over NCCL; the step is one captured CUDA graph "
                         "(training.GraphedTrainStep)",

@@ -249,11 +249,16 @@ def train_step(args, model, optim, nodes_dist, x, h, node_mask, edge_mask, conte
 
 
 class GraphedTrainStep:
-    """train_step (zero, loss, backward, bucketed all-reduce, adaptive clipping, AdamW, EMA) captured ONCE as a CUDA graph
+    """train_step (zero, loss, gradients, bucketed all-reduce, adaptive clipping, AdamW, EMA) captured ONCE as a CUDA graph
     for a fixed batch signature (the molecule sizes, i.e. node_mask / edge_mask) and replayed per step: the ~3000 kernel
     launches of the eager step cost one graph launch, no host synchronisation happens inside the step (the gradient-norm
     history lives on the device: DeviceGradClip), and the step's inputs are copied into static buffers.  Batches with
     another signature need their own instance (or the eager `train_step`).
+
+    Autograd binds a parameter's AccumulateGrad node to the stream on which it was created; the warm-up here runs on the
+    side stream the capture uses, so fresh nodes are fine.  An autograd graph from an EARLIER backward on the default stream
+    that is still referenced (e.g. a loss tensor that was not detached) keeps legacy-stream nodes alive and makes the capture
+    fail with cudaErrorStreamCaptureImplicit: drop such references first.
 
     The optimiser must have been built with `capturable=True` (get_optim(..., capturable=True))."""
 
@@ -274,13 +279,14 @@ class GraphedTrainStep:
         model.train()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                                  # eager warm-up on a side stream (caches, NCCL, AdamW state)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(side):                                  # eager warm-up on the stream the capture will use
             for _ in range(max(1, warmup)):                            # >= 1: mask packing and lazy state need host work
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.nll, self.grad_norm = self._body()
 
     def _body(self):
@@ -295,6 +301,13 @@ class GraphedTrainStep:
         if self.ema is not None and self.model_ema is not None and getattr(self.args, "ema_decay", 0) > 0:
             self.ema.update_model_average(self.model_ema, self.model)
         return nll.detach(), grad_norm
+
+    def close(self):
+        """Release the captured graph (it holds NCCL work when the step all-reduces: destroy it BEFORE
+        torch.distributed.destroy_process_group, which otherwise waits forever)."""
+        torch.cuda.synchronize()
+        self.graph = None
+        self.nll = self.grad_norm = None
 
     def __call__(self, x, h=None, context=None):
         """Copies the step's inputs into the static buffers (asynchronously) and replays the graph.  Returns device

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--nf", type=int, default=192)
     ap.add_argument("--n-layers", type=int, default=9)
+    ap.add_argument("--graph", action="store_true", help="time training.GraphedTrainStep instead of the eager train_step")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -100,14 +101,21 @@ def main():
     report.update(allreduce_bytes=nbytes, grad_vs_whole_batch=worst)
     assert worst < 2e-5, worst
     model.zero_grad(set_to_none=True)
+    del nll_all, mine, nll                         # no autograd graph of the default stream survives into a capture
     # ---- timed steps --------------------------------------------------------------------------------------------------
-    optim = training.get_optim(args, model)
+    graphed = "--graph" in sys.argv                # the step as ONE captured CUDA graph (training.GraphedTrainStep)
+    optim = training.get_optim(args, model, capturable=graphed)
     buckets = training.FlatGradBuckets(model)      # timed steps: flat gradients, all-reduce overlapped with backward
     q = training.Queue()
     q.add(3000.0)
     model_ema = copy.deepcopy(model)
     ema = training.EMA(args.ema_decay)
     x, h, nm, em, ctx, draws = shard(sl)
+    gstep = None
+    if graphed:
+        gstep = training.GraphedTrainStep(args, model, optim, nodes_dist, x, h, nm, em, ctx, model_ema=model_ema, ema=ema,
+                                          buckets=buckets)
+    report["graphed"] = graphed
     times = []
     for it in range(a.steps + 2):
         if world > 1:
@@ -115,8 +123,11 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        nll, gn = training.train_step(args, model, optim, nodes_dist, x, h, nm, em, ctx, gradnorm_queue=q,
-                                      model_ema=model_ema, ema=ema, buckets=buckets)
+        if gstep is not None:
+            nll, gn = gstep(x, h, ctx)
+        else:
+            nll, gn = training.train_step(args, model, optim, nodes_dist, x, h, nm, em, ctx, gradnorm_queue=q,
+                                          model_ema=model_ema, ema=ema, buckets=buckets)
         e1.record()
         torch.cuda.synchronize()
         if it >= 2:
@@ -138,6 +149,8 @@ def main():
         os.makedirs("gpurun_out", exist_ok=True)
         with open(f"gpurun_out/train_check_n{world}.json", "w") as f:
             json.dump(report, f)
+    if gstep is not None:
+        gstep.close()                               # the graph holds NCCL work: release it before the process group
     if world > 1:
         dist.destroy_process_group()
 
