@@ -158,6 +158,24 @@ __device__ __forceinline__ EdgeGeom edge_geom(const float* __restrict__ x, const
   return g;
 }
 
+// ---- per-device launch configuration -----------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: a process that drives several GPUs
+// configures each kernel instantiation once per device ordinal (small fixed table; ordinals past it reconfigure every time).
+constexpr int GEOLDM_MAX_DEVICES = 32;
+struct DeviceOnce {
+  bool done[GEOLDM_MAX_DEVICES] = {};
+  int sm_count[GEOLDM_MAX_DEVICES] = {};
+};
+// returns the current device ordinal clamped into the table, sets `fresh` when this (kernel, device) pair is new
+inline int device_slot(DeviceOnce& st, bool& fresh) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < GEOLDM_MAX_DEVICES) ? dev : GEOLDM_MAX_DEVICES - 1;
+  fresh = !st.done[slot] || slot != dev;
+  if (fresh) cudaDeviceGetAttribute(&st.sm_count[slot], cudaDevAttrMultiProcessorCount, dev);
+  return slot;
+}
+
 // ---- launchers implemented in the .cu files ----------------------------------------------------
 int launch_edge_simt(const geoldm_egnn_config& cfg, const geoldm_edge_mlp& w, const geoldm_batch& b, bool equiv,
                      const float* pq, const float* x, const float* x0, float* out, cudaStream_t st);

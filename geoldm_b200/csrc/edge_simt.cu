@@ -303,11 +303,13 @@ __global__ void __launch_bounds__(NT, 2) edge_simt_kernel(const EdgeSimtArgs a) 
 template <int H>
 int launch_h(const EdgeSimtArgs& args, bool equiv, int n_tile, cudaStream_t st) {
   constexpr size_t smem = edge_simt_smem_bytes<H>();
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  bool fresh;
+  const int slot = device_slot(once, fresh);
+  if (fresh) {
     cudaFuncSetAttribute(edge_simt_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(edge_simt_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    once.done[slot] = true;
   }
   if (equiv)
     edge_simt_kernel<H, true><<<n_tile, NT, smem, st>>>(args);

@@ -690,19 +690,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 template <int H, int MODE, int CS, bool PAIR>
 int launch_mode(const TcArgs& a, cudaStream_t st) {
   using S = Smem<H, MODE>;
-  static int sm_count = 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  bool fresh;
+  const int slot = device_slot(once, fresh);
+  if (fresh) {
     cudaError_t e = cudaFuncSetAttribute(tc_kernel<H, MODE, CS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
     if (e != cudaSuccess) {
       set_error("tc_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
       return -2;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    once.done[slot] = true;
   }
+  const int sm_count = once.sm_count[slot];
   GEOLDM_REQUIRE(a.n_slabs % 2 == 0, "tc_kernel: K/32 = %d must be even", a.n_slabs);
   const int n_tile_pad = (a.n_tile + CS - 1) / CS * CS;
   const int work = n_tile_pad * a.n_blocks;     // in 128-row tiles (a PAIR work item covers two of them)

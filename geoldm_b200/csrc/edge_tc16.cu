@@ -997,19 +997,18 @@ int make_stage_maps(const float* pq, int pq_ld, int n_node, int H, StageMaps& ou
 template <int H, int MODE>
 int launch_mode(const Args& a, cudaStream_t st, const StageMaps* sm = nullptr) {
   using S = Smem<H, MODE>;
-  static int sm_count = 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  bool fresh;
+  const int slot = device_slot(once, fresh);
+  if (fresh) {
     cudaError_t e = cudaFuncSetAttribute(tc16_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
     if (e != cudaSuccess) {
       set_error("tc16_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
       return -2;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    once.done[slot] = true;
   }
+  const int sm_count = once.sm_count[slot];
   if (a.n_tile == 0) return 0;
   const int work = (a.n_tile + 1) / 2 * 2 * a.n_blocks;
   int grid = work < sm_count ? work : sm_count;
@@ -1520,19 +1519,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain16_kernel(const ChainAr
 template <int H>
 int launch_chain(const ChainArgs& a, cudaStream_t st) {
   using S = ChainSmem<H>;
-  static int sm_count = 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  bool fresh;
+  const int slot = device_slot(once, fresh);
+  if (fresh) {
     cudaError_t e = cudaFuncSetAttribute(chain16_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::ALLOC);
     if (e != cudaSuccess) {
       set_error("chain16_kernel: cannot reserve %u bytes of shared memory: %s", S::ALLOC, cudaGetErrorString(e));
       return -2;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    once.done[slot] = true;
   }
+  const int sm_count = once.sm_count[slot];
   if (a.n_tile == 0) return 0;
   const int work = (a.n_tile + 1) / 2 * 2;
   int grid = work < sm_count ? work : sm_count;
