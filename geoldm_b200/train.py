@@ -27,14 +27,53 @@ def _stream(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+# Edge-level GEMMs (M = number of edges) of the autograd path run on the tcgen05 fp16-split kernel (fp32-equivalent
+# products, csrc/edge_tc16.cu DENSE mode) in the forward and input-gradient directions; node-level ones (a few tiles) stay
+# on the fp32 FFMA kernel, whose launch is cheaper than packing a weight image.  GEOLDM_TRAIN_TC=0 disables it.
+_TC_MIN_ROWS = 4096
+
+
+def _tc_block(n: int) -> int:
+    """Column-block width H of the tensor-core kernel for n outputs (0: not usable)."""
+    for hb in (256, 192, 128, 64):
+        if n % hb == 0:
+            return hb
+    return 0
+
+
+def _tc_ok(M: int, K: int, N: int) -> bool:
+    import os
+    return (M >= _TC_MIN_ROWS and K % 64 == 0 and _tc_block(N) > 0 and os.environ.get("GEOLDM_TRAIN_TC", "1") != "0"
+            and _lib.lib().geoldm_has_tcgen05() == 1)
+
+
+def _tc_linear(x, w_nk, bias, M, K, N):
+    """x [M,K] @ w_nk[N,K]^T (+ bias) through geoldm_tc_pack16 + geoldm_linear_tc (3xF16)."""
+    L = _lib.lib()
+    hb = _tc_block(N)
+    st = _stream(x)
+    pack = torch.empty(L.geoldm_tc_pack16_bytes(hb, N, K), dtype=torch.uint8, device=x.device)
+    _lib.check(L.geoldm_tc_pack16(hb, _lib.ptr(w_nk), N, K, _lib.ptr(pack), st), "geoldm_tc_pack16(train)")
+    out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    _lib.check(L.geoldm_linear_tc(hb, 16, _lib.ptr(x), K, None, 0, 1.0, _lib.ptr(pack), N // hb, _lib.ptr(bias), None, 0,
+                                  _lib.ptr(out), M, st), "geoldm_linear_tc(train)")
+    return out
+
+
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b on the geoldm_b200 GEMM kernels (fp32 FFMA), x [M,K], W [N,K] (PyTorch layout)."""
+    """y = x W^T + b on the geoldm_b200 GEMM kernels, x [M,K], W [N,K] (PyTorch layout): fp16-split tcgen05 for edge-level
+    row counts (forward and dX), fp32 FFMA otherwise and for dW."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         x = x.contiguous()
         M, K = x.shape
         N = weight.shape[0]
+        if x.is_cuda and _tc_ok(M, K, N):
+            out = _tc_linear(x, weight.contiguous(), bias, M, K, N)
+            ctx.save_for_backward(x, weight)
+            ctx.has_bias = bias is not None
+            return out
         wt = weight.t().contiguous()                      # k-major [K][N]
         out = torch.empty(M, N, device=x.device, dtype=torch.float32)
         _lib.check(_lib.lib().geoldm_linear(_lib.ptr(x), K, None, 0, 1.0, _lib.ptr(wt), _lib.ptr(bias), None, 0,
@@ -51,7 +90,9 @@ class _LinearFn(torch.autograd.Function):
         N = weight.shape[0]
         L = _lib.lib()
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and x.is_cuda and _tc_ok(M, N, K):
+            dx = _tc_linear(dy, weight.t().contiguous(), None, M, N, K)     # dX = dY W = dY (W^T)^T
+        elif ctx.needs_input_grad[0]:
             w = weight.contiguous()                       # [N][K] is already k-major for dX = dY W
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
             _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
