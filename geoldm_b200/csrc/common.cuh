@@ -92,34 +92,6 @@ __device__ __forceinline__ void silu_x4(f32x2& A, f32x2& B) {
   B = mul2(B, mul2(r, dA));
 }
 
-// SiLU of eight values (four packed pairs), ONE reciprocal per four values: 1.25 MUFU operations per value.
-//   r = 1 / (dA dB dC dD); 1/dA = r (dC dD) dB, ...   Exponent clamped at 30 (product <= 2^121): for v < -20.8
-//   sigmoid(v) reads 2^-30 instead of e^v, absolute error of SiLU < 1e-9 |v|.
-__device__ __forceinline__ void silu_x8(f32x2& A, f32x2& B, f32x2& C, f32x2& D) {
-  const f32x2 nl2e = pk2(-1.4426950408889634f, -1.4426950408889634f);
-  const f32x2 one = pk2(1.0f, 1.0f);
-  float a0, a1, b0, b1, c0, c1, d0, d1;
-  upk2(mul2(A, nl2e), a0, a1);
-  upk2(mul2(B, nl2e), b0, b1);
-  upk2(mul2(C, nl2e), c0, c1);
-  upk2(mul2(D, nl2e), d0, d1);
-  a0 = ex2_ftz(fminf(a0, 30.0f)); a1 = ex2_ftz(fminf(a1, 30.0f));
-  b0 = ex2_ftz(fminf(b0, 30.0f)); b1 = ex2_ftz(fminf(b1, 30.0f));
-  c0 = ex2_ftz(fminf(c0, 30.0f)); c1 = ex2_ftz(fminf(c1, 30.0f));
-  d0 = ex2_ftz(fminf(d0, 30.0f)); d1 = ex2_ftz(fminf(d1, 30.0f));
-  const f32x2 dA = add2(pk2(a0, a1), one), dB = add2(pk2(b0, b1), one);
-  const f32x2 dC = add2(pk2(c0, c1), one), dD = add2(pk2(d0, d1), one);
-  const f32x2 pAB = mul2(dA, dB), pCD = mul2(dC, dD);
-  float p0, p1;
-  upk2(mul2(pAB, pCD), p0, p1);
-  const f32x2 r = pk2(rcp_ftz(p0), rcp_ftz(p1));
-  const f32x2 rAB = mul2(r, pCD), rCD = mul2(r, pAB);
-  A = mul2(A, mul2(rAB, dB));
-  B = mul2(B, mul2(rAB, dA));
-  C = mul2(C, mul2(rCD, dD));
-  D = mul2(D, mul2(rCD, dC));
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

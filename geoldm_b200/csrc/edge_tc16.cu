@@ -473,15 +473,6 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
             WR[0] = pk2(r0.x, r0.y); WR[1] = pk2(r0.z, r0.w); WR[2] = pk2(r1.x, r1.y); WR[3] = pk2(r1.z, r1.w);
             WD[0] = pk2(d0.x, d0.y); WD[1] = pk2(d0.z, d0.w); WD[2] = pk2(d1.x, d1.y); WD[3] = pk2(d1.z, d1.w);
           }
-#ifdef GEOLDM_TC16_PREFETCH
-          if (s + 1 < n_slabs_p) {
-#pragma unroll
-            for (int p = 0; p < ROWS_PT; ++p) {
-              prefetch_l1(pQ[p] + k0 + BK);
-              if ((lmask >> p) & 1u) prefetch_l1(pP[p] + k0 + BK);
-            }
-          }
-#endif
           float4 Pc0 = make_float4(0.f, 0.f, 0.f, 0.f), Pc1 = Pc0;
 #pragma unroll
           for (int ph = 0; ph < ROWS_PT / 2; ++ph) {   // the Q rows of two tile rows in flight at a time
@@ -511,12 +502,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
               f32x2 e1 = fma2(WD[1], D2, fma2(WR[1], R2, add2(pk2(Pc0.z, Pc0.w), pk2(q[pp][0].z, q[pp][0].w))));
               f32x2 e2 = fma2(WD[2], D2, fma2(WR[2], R2, add2(pk2(Pc1.x, Pc1.y), pk2(q[pp][1].x, q[pp][1].y))));
               f32x2 e3 = fma2(WD[3], D2, fma2(WR[3], R2, add2(pk2(Pc1.z, Pc1.w), pk2(q[pp][1].z, q[pp][1].w))));
-#ifdef GEOLDM_SILU_QUAD
-              silu_x8(e0, e1, e2, e3);
-#else
               silu_x4(e0, e1);
               silu_x4(e2, e3);
-#endif
               split_f16x2(e0, hi.x, lo.x); split_f16x2(e1, hi.y, lo.y);
               split_f16x2(e2, hi.z, lo.z); split_f16x2(e3, hi.w, lo.w);
               const uint32_t off = sw128_off(r, chunk);
@@ -814,9 +801,11 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
           const f32x2 g2 = pk2(g, g);
           TC_PROF(const long long te4 = clock64(); te_bar += te4 - te3;)
           // ---- pass 2: e = m * gate, summed over each receiver run of this warp's 32 rows -------------------------
-          // 32 x 32 chunks go through this warp's [32][36] fp32 transposition tile; lane (half, cp) then sums columns
-          // 2 cp, 2 cp + 1 over every second row of the run (64-bit loads), the two halves are folded with one shuffle
-          // and leave as one vector reduction per (run, column pair).  The summation order is fixed.
+          // 32 x 32 chunks go through this warp's [32][36] fp32 transposition tile.  Static path: lane (grp, c4) owns the
+          // 8-row group grp and 4 columns, multiplies by the row gates inside an unrolled 8-step sum, exchanges the partial
+          // sum of a run that continues into the next group through the tile's pad columns and emits one 16-byte vector
+          // reduction per (run, 4 columns).  Generic path (runs shorter than 8 rows): lane (half, cp) sums columns 2 cp,
+          // 2 cp + 1 over every second row of a run.  The summation order is fixed in both.
           const uint32_t Tw = sbase + S::OFF_T + warp * (32 * 36 * 4);
           // Run structure of this warp's 32 rows, seen by lane (grp, c4): row group [8 grp, 8 grp + 8) x columns 4 c4 .. +3 of
           // a chunk.  The first invalid row closes the last run (its "receiver" is -1: nothing is emitted for it).
@@ -1388,8 +1377,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain16_kernel(const ChainAr
     for (int iter = 0; iter < n_iter; ++iter) {
       int row0, nrows;
       tile_of(iter, row0, nrows);
-      const bool valid = r < nrows;
-      const size_t grow = (size_t)(row0 + (valid ? r : 0));
       // ---- epilogue 1: t1 = SiLU(scale D + b1) -> image ------------------------------------------------------------------
       {
         const int region = acc_it & 1;
