@@ -243,13 +243,16 @@ def test_node_chain_kernel(dev, H, m, nb):
     assert torch.equal(Hd.cpu(), h)                  # inputs untouched
 
 
-def test_forward_with_fused_node_chain_subprocess(dev):
-    """The opt-in fused node chain inside the whole forward (GEOLDM_TC_CHAIN=1 is read once per process): the QM9 / GEOM /
-    flag-variant forward goldens in the default arithmetic, in a child process with the switch set."""
+@pytest.mark.parametrize("switch", ["GEOLDM_TC_CHAIN=1", "GEOLDM_TC_STAGE=0"])
+def test_forward_with_library_switches_subprocess(dev, switch):
+    """Library switches that are read once per process, each in a child process: the opt-in fused node chain
+    (GEOLDM_TC_CHAIN=1) and the per-edge gather path of the edge kernels (GEOLDM_TC_STAGE=0, what a caller without
+    geoldm_batch.tile_meta gets) against the QM9 / GEOM / flag-variant forward goldens in the default arithmetic."""
     import subprocess, sys
     if not _has_tc():
         pytest.skip("tcgen05 kernels not built")
-    env = dict(os.environ, GEOLDM_TC_CHAIN="1")
+    key, val = switch.split("=")
+    env = dict(os.environ, **{key: val})
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
                         "(qm9_forward_golden or geom_forward_golden or flag_variants_golden) and 3xf16"],
