@@ -28,8 +28,9 @@ def _stream(t):
 
 
 # Edge-level GEMMs (M = number of edges) of the autograd path run on the tcgen05 fp16-split kernel (fp32-equivalent
-# products, csrc/edge_tc16.cu DENSE mode) in the forward and input-gradient directions; node-level ones (a few tiles) stay
-# on the fp32 FFMA kernel, whose launch is cheaper than packing a weight image.  GEOLDM_TRAIN_TC=0 disables it.
+# products, csrc/edge_tc16.cu DENSE mode) in the FORWARD direction, where the A operand is an O(1) activation; input and
+# weight gradients stay on the fp32 FFMA kernels (gradient operands underflow fp16, see _LinearFn.backward), as do the
+# node-level GEMMs (a few tiles: the launch is cheaper than packing a weight image).  GEOLDM_TRAIN_TC=0 disables it.
 _TC_MIN_ROWS = 4096
 
 
@@ -61,8 +62,8 @@ def _tc_linear(x, w_nk, bias, M, K, N):
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b on the geoldm_b200 GEMM kernels, x [M,K], W [N,K] (PyTorch layout): fp16-split tcgen05 for edge-level
-    row counts (forward and dX), fp32 FFMA otherwise and for dW."""
+    """y = x W^T + b on the geoldm_b200 GEMM kernels, x [M,K], W [N,K] (PyTorch layout): fp16-split tcgen05 for the forward
+    at edge-level row counts, fp32 FFMA otherwise and for dX / dW."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -90,9 +91,10 @@ class _LinearFn(torch.autograd.Function):
         N = weight.shape[0]
         L = _lib.lib()
         dx = dw = db = None
-        if ctx.needs_input_grad[0] and x.is_cuda and _tc_ok(M, N, K):
-            dx = _tc_linear(dy, weight.t().contiguous(), None, M, N, K)     # dX = dY W = dY (W^T)^T
-        elif ctx.needs_input_grad[0]:
+        # dX stays on the fp32 FFMA kernel: its A operand is a GRADIENT, whose magnitude scales with 1 / batch size and
+        # falls below the normal fp16 range (6e-5) - the fp16-split products then lose their low halves.  Measured: fine
+        # at 64 molecules, 4.7 relative error on a bias gradient at 256 molecules per GPU (scripts/train_check.py).
+        if ctx.needs_input_grad[0]:
             w = weight.contiguous()                       # [N][K] is already k-major for dX = dY W
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
             _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
