@@ -111,6 +111,93 @@ __global__ void __launch_bounds__(NT, 2) linear_kernel(const LinArgs a) {
     }
   }
 }
+
+// Same contraction for node-level row counts (a few thousand rows): 32 x 64 tiles, 128 threads, 4 x 4 outputs per thread.
+// At m = 1158 (64 QM9 molecules) the 128 x 64 tiles above are 30 CTAs on 148 SMs, each walking the whole K loop: 18 us per
+// launch, 144 launches per training step; four times as many, four times shorter CTAs bring that to the launch-latency floor.
+constexpr int SBM = 32, SNT = 128, SAST = SBM + 4;
+template <int EPI>
+__global__ void __launch_bounds__(SNT, 8) linear_small_kernel(const LinArgs a) {
+  __shared__ __align__(16) float As[2][BK][SAST];
+  __shared__ __align__(16) float Ws[2][BK][BN];
+  const int t = threadIdx.x;
+  const int rg = t >> 4, cg = t & 15;            // 8 x 16 thread grid, 4 x 4 outputs each
+  const int row0 = blockIdx.y * SBM, col0 = blockIdx.x * BN;
+  const int K = a.k1 + a.k2, NS = K / BK;
+  const int lrow = t >> 2, lk = (t & 3) * 4;     // activation loader: (row, 4 consecutive k)
+  const bool lvalid = row0 + lrow < a.m;
+  const int wk = t >> 4, wc4 = (t & 15) * 4;     // weight loader: rows wk and wk + 8 of the slab, 4 consecutive columns
+  const bool wvalid = col0 + wc4 < a.n;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  float4 pf;
+  auto a_load = [&](int s) {
+    pf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lvalid) {
+      const int k0 = s * BK + lk;
+      const float* src = (k0 < a.k1) ? a.a1 + (size_t)(row0 + lrow) * a.k1 + k0
+                                     : a.a2 + (size_t)(row0 + lrow) * a.k2 + (k0 - a.k1);
+      pf = __ldg(reinterpret_cast<const float4*>(src));
+      if (k0 >= a.k1 && a.a2_div != 1.0f) {
+        const float d = a.a2_div;
+        pf.x = __fdiv_rn(pf.x, d); pf.y = __fdiv_rn(pf.y, d); pf.z = __fdiv_rn(pf.z, d); pf.w = __fdiv_rn(pf.w, d);
+      }
+    }
+  };
+  auto a_store = [&](int buf) {
+    As[buf][lk][lrow] = pf.x; As[buf][lk + 1][lrow] = pf.y; As[buf][lk + 2][lrow] = pf.z; As[buf][lk + 3][lrow] = pf.w;
+  };
+  auto w_load = [&](int s, int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = wk + 8 * h;
+      if (wvalid) cp_async16(&Ws[buf][kk][wc4], a.wt + (size_t)(s * BK + kk) * a.n + col0 + wc4);
+      else *reinterpret_cast<float4*>(&Ws[buf][kk][wc4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+  w_load(0, 0);
+  a_load(0);
+  a_store(0);
+  for (int s = 0; s < NS; ++s) {
+    const int buf = s & 1;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (s + 1 < NS) { w_load(s + 1, buf ^ 1); a_load(s + 1); }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av4 = *reinterpret_cast<const float4*>(&As[buf][k][rg * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][cg * 4]);
+      const float av[4] = {av4.x, av4.y, av4.z, av4.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    if (s + 1 < NS) a_store(buf ^ 1);
+  }
+  const int col = col0 + cg * 4;
+  if (col < a.n) {
+    const float4 bias = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = row0 + rg * 4 + r;
+      if (row < a.m) {
+        float4 o = make_float4(acc[r][0] + bias.x, acc[r][1] + bias.y, acc[r][2] + bias.z, acc[r][3] + bias.w);
+        if (EPI == 1) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+        if (EPI == 2) {
+          const float4 rs = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)row * a.n + col));
+          o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+        }
+        *reinterpret_cast<float4*>(a.out + (size_t)row * a.n + col) = o;
+      }
+    }
+  }
+}
 }  // namespace
 
 int launch_linear(const float* a1, int k1, const float* a2, int k2, float a2_div, const float* wt,
@@ -120,6 +207,20 @@ int launch_linear(const float* a1, int k1, const float* a2, int k2, float a2_div
   GEOLDM_REQUIRE(epi != 2 || res != nullptr, "linear: residual epilogue needs res");
   if (m == 0) return 0;
   LinArgs a{a1, a2, wt, bias, res, out, k1, k2, m, n, a2_div};
+#ifndef GEOLDM_LINEAR_SMALL_M
+#define GEOLDM_LINEAR_SMALL_M 8192
+#endif
+  if (m <= GEOLDM_LINEAR_SMALL_M) {   // node-level row counts: small tiles fill the SMs
+    dim3 sgrid((n + BN - 1) / BN, (m + SBM - 1) / SBM);
+    switch (epi) {
+      case 0: linear_small_kernel<0><<<sgrid, SNT, 0, st>>>(a); break;
+      case 1: linear_small_kernel<1><<<sgrid, SNT, 0, st>>>(a); break;
+      case 2: linear_small_kernel<2><<<sgrid, SNT, 0, st>>>(a); break;
+      default: set_error("linear: bad epilogue %d", epi); return -1;
+    }
+    GEOLDM_CHECK_LAUNCH("linear_small_kernel");
+    return 0;
+  }
   dim3 grid((n + BN - 1) / BN, (m + BM - 1) / BM);
   switch (epi) {
     case 0: linear_kernel<0><<<grid, NT, 0, st>>>(a); break;
