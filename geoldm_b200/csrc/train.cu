@@ -26,26 +26,32 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  auto load = [&](int mrow, int buf) {
-    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+  // global -> registers (issued before the FMAs of the current slab) -> shared (after them): the L2 latency of the next
+  // 16-row slab is hidden behind 256 FMAs per thread instead of being exposed at every slab
+  float4 va, vb;
+  auto g_load = [&](int mrow) {
+    va = make_float4(0.f, 0.f, 0.f, 0.f); vb = va;
     const int mm = mrow + lr;
     if (mm < m_end) {
       const float* pa = a + (size_t)mm * lda + n0 + lc;
       const float* pb = b + (size_t)mm * ldb + k0 + lc;
-      if (n0 + lc + 3 < n) va = *reinterpret_cast<const float4*>(pa);
+      if (n0 + lc + 3 < n) va = __ldg(reinterpret_cast<const float4*>(pa));
       else { float tmp[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (n0 + lc + e < n) tmp[e] = pa[e]; va = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]); }
-      if (k0 + lc + 3 < k) vb = *reinterpret_cast<const float4*>(pb);
+      if (k0 + lc + 3 < k) vb = __ldg(reinterpret_cast<const float4*>(pb));
       else { float tmp[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (k0 + lc + e < k) tmp[e] = pb[e]; vb = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]); }
     }
+  };
+  auto s_store = [&](int buf) {
     *reinterpret_cast<float4*>(&As[buf][lr][lc]) = va;
     *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = vb;
   };
 
   int buf = 0;
-  if (m_begin < m_end) load(m_begin, 0);
+  if (m_begin < m_end) { g_load(m_begin); s_store(0); }
   __syncthreads();
   for (int mrow = m_begin; mrow < m_end; mrow += TN_BM) {
-    if (mrow + TN_BM < m_end) load(mrow + TN_BM, buf ^ 1);
+    const bool more = mrow + TN_BM < m_end;
+    if (more) g_load(mrow + TN_BM);
 #pragma unroll
     for (int mm = 0; mm < TN_BM; ++mm) {
       const float4 av = *reinterpret_cast<const float4*>(&As[buf][mm][tr * 4]);
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
+    if (more) s_store(buf ^ 1);
     __syncthreads();
     buf ^= 1;
   }
