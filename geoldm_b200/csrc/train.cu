@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 // Fused element-wise stages of the edge MLPs for the autograd path (train.py): one warp per edge, lanes stride over the
 // H columns (coalesced 128-byte rows), everything recomputed from the GEMM inputs/outputs in the backward pass so that
-// no [E, H] intermediate besides the GEMM operands is kept.  Accurate expf (training is not the hot loop).
+// no [E, H] intermediate besides the GEMM operands is kept.  ex2.approx sigmoid with a correctly rounded division.
 //   act   : a[e][k] = SiLU(P[i_e][k] + Q[j_e][k] + r_e w_r[k] + d0_e w_d[k])                  (egnn_new.py:30-36, split form)
 //   tail  : m = SiLU(mpre + b2);  gate: agg[i_e] += m sigmoid(m.w_att + b_att) / div        (:37-44, :258-267)
 //           head: sc[e] = m.w                                                                 (:86-90)
@@ -92,7 +92,20 @@ namespace geoldm {
 namespace {
 constexpr int MAXC = 8;   // columns per lane: H <= 256
 
-__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+// ex2.approx (2 ulp) + correctly rounded division: with rcp.approx as well the worst config-5 gradient tensor moved from
+// 6e-6 to 1.03e-5 of the fp64 reference run (north_star's tolerance is 1e-5), with accurate expf the kernels are 10 % slower
+#ifndef GEOLDM_TRAIN_SIGM
+#define GEOLDM_TRAIN_SIGM 2
+#endif
+__device__ __forceinline__ float sigm(float v) {
+#if GEOLDM_TRAIN_SIGM == 0
+  return 1.0f / (1.0f + expf(-v));
+#elif GEOLDM_TRAIN_SIGM == 1
+  return sigmoidf_(v);
+#else
+  return __fdiv_rn(1.0f, 1.0f + ex2_ftz(v * -1.4426950408889634f));
+#endif
+}
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -140,11 +153,26 @@ __global__ void edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, 
                                     float* __restrict__ dw_rd) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-  float acc_r[MAXC], acc_d[MAXC];
+  float acc_r[MAXC], acc_d[MAXC], acc_p[MAXC];
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) acc_r[k] = acc_d[k] = 0.f;
-  for (int e = warp; e < E; e += nwarp) {
+  for (int k = 0; k < MAXC; ++k) acc_r[k] = acc_d[k] = acc_p[k] = 0.f;
+  // a warp owns a CONTIGUOUS range of edge rows: rows are sorted by receiver, so the receiver-side gradient dP_i is summed
+  // in registers over the run (fixed order) and leaves as one atomic per (run piece, column) instead of one per edge
+  const int per = (E + nwarp - 1) / nwarp;
+  const int e_begin = min(E, warp * per), e_end = min(E, e_begin + per);
+  int cur_i = -1;
+  auto flush_p = [&]() {
+    if (cur_i < 0) return;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H) atomicAdd(dpq + (size_t)cur_i * pq_ld + c, acc_p[k]);
+      acc_p[k] = 0.f;
+    }
+  };
+  for (int e = e_begin; e < e_end; ++e) {
     const int i = ei[e], j = ej[e];
+    if (i != cur_i) { flush_p(); cur_i = i; }
     const float* P = pq + (size_t)i * pq_ld;
     const float* Q = pq + (size_t)j * pq_ld + H;
     const float re = r[e], de = d0[e];
@@ -157,7 +185,7 @@ __global__ void edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, 
         const float z = P[c] + Q[c] + re * wr + de * wd;
         const float s = sigm(z);
         const float g = da[(size_t)e * H + c] * (s * (1.0f + z * (1.0f - s)));     // d SiLU / dz
-        atomicAdd(dpq + (size_t)i * pq_ld + c, g);
+        acc_p[k] += g;
         atomicAdd(dpq + (size_t)j * pq_ld + H + c, g);
         sr += g * wr; sd += g * wd;
         acc_r[k] += g * re; acc_d[k] += g * de;
@@ -166,6 +194,7 @@ __global__ void edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, 
     sr = warp_sum_f(sr); sd = warp_sum_f(sd);
     if (lane == 0) { dr[e] = sr; dd0[e] = sd; }
   }
+  flush_p();
   __shared__ float red[TRAIN_WARPS][32 * MAXC];
   block_column_add(red, acc_r, H, dw_rd);
   block_column_add(red, acc_d, H, dw_rd + H);
@@ -178,7 +207,24 @@ __global__ void edge_tail_fwd_kernel(int E, int H, const float* __restrict__ mpr
                                      float* __restrict__ sc) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-  for (int e = warp; e < E; e += nwarp) {
+  // contiguous edge range per warp: the messages of a receiver run are summed in registers (fixed order), one atomic per
+  // (run piece, column)
+  const int per = (E + nwarp - 1) / nwarp;
+  const int e_begin = min(E, warp * per), e_end = min(E, e_begin + per);
+  int cur_i = -1;
+  float acc_a[MAXC];
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) acc_a[k] = 0.f;
+  auto flush_a = [&]() {
+    if (cur_i < 0) return;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < H) atomicAdd(agg + (size_t)cur_i * H + c, acc_a[k]);
+      acc_a[k] = 0.f;
+    }
+  };
+  for (int e = e_begin; e < e_end; ++e) {
     float m[MAXC];
     float dot = 0.f;
 #pragma unroll
@@ -194,24 +240,23 @@ __global__ void edge_tail_fwd_kernel(int E, int H, const float* __restrict__ mpr
     dot = warp_sum_f(dot);
     if (!gate) { if (lane == 0) sc[e] = dot; continue; }
     const float g = attention ? sigm(dot + bw[0]) : 1.0f;
-    float* out = agg + (size_t)ei[e] * H;
+    const int i = ei[e];
+    if (i != cur_i) { flush_a(); cur_i = i; }
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      if (c < H) atomicAdd(out + c, m[k] * g * inv_div);
-    }
+    for (int k = 0; k < MAXC; ++k) acc_a[k] += m[k] * g * inv_div;
   }
+  if (gate) flush_a();
 }
 
 __global__ void edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpre, const float* __restrict__ b2,
                                      const float* __restrict__ w, const float* __restrict__ bw, int gate, int attention,
                                      const int* __restrict__ ei, float inv_div, const float* __restrict__ dagg,
                                      const float* __restrict__ dsc, float* __restrict__ dmpre, float* __restrict__ db2,
-                                     float* __restrict__ dw, float* __restrict__ dbw) {
+                                     float* __restrict__ dw, float* __restrict__ dbw, double* __restrict__ bw_scratch) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
   float acc_b[MAXC], acc_w[MAXC];
-  float acc_bw = 0.f;
+  double acc_bw = 0.0;      // attention-bias gradient: a cancelling sum over ALL edges, kept in double and summed in a fixed order
 #pragma unroll
   for (int k = 0; k < MAXC; ++k) acc_b[k] = acc_w[k] = 0.f;
   for (int e = warp; e < E; e += nwarp) {
@@ -240,7 +285,7 @@ __global__ void edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpr
     } else {
       ds = dsc[e];
     }
-    if (lane == 0 && dbw) acc_bw += ds;
+    if (lane == 0 && dbw) acc_bw += (double)ds;
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) {
       const int c = lane + 32 * k;
@@ -256,14 +301,35 @@ __global__ void edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpr
   __shared__ float red[TRAIN_WARPS][32 * MAXC];
   block_column_add(red, acc_b, H, db2);
   if (dw) block_column_add(red, acc_w, H, dw);
-  if (dbw) {                                     // one atomic per block for the scalar bias gradient
-    if (lane == 0) red[threadIdx.x >> 5][0] = acc_bw;
+  if (dbw) {
+    // block partial (double, fixed warp order) -> scratch[block]; the LAST block to finish adds all partials in block order
+    // and accumulates the total into dbw: deterministic and accurate to double rounding.  (Float atomics in arrival order
+    // made this 5e-6-sized scalar wander by up to 3e-5 relative from run to run.)
+    __shared__ double red_bw[TRAIN_WARPS];
+    __shared__ bool is_last;
+    if (lane == 0) red_bw[threadIdx.x >> 5] = acc_bw;
     __syncthreads();
     if (threadIdx.x == 0) {
-      float v = 0.f;
+      double v = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < TRAIN_WARPS; ++ww) v += red[ww][0];
-      atomicAdd(dbw, v);
+      for (int ww = 0; ww < TRAIN_WARPS; ++ww) v += red_bw[ww];
+      if (bw_scratch) {
+        bw_scratch[blockIdx.x] = v;
+        __threadfence();
+        unsigned* counter = reinterpret_cast<unsigned*>(bw_scratch + gridDim.x);
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+      } else {
+        atomicAdd(dbw, (float)v);
+        is_last = false;
+      }
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+      __threadfence();
+      double total = 0.0;
+      for (unsigned bb = 0; bb < gridDim.x; ++bb) total += reinterpret_cast<volatile double*>(bw_scratch)[bb];
+      dbw[0] += (float)total;
+      *reinterpret_cast<unsigned*>(bw_scratch + gridDim.x) = 0u;        // the scratch is reusable
     }
   }
 }
@@ -308,25 +374,28 @@ int geoldm_train_edge_tail_fwd(int n_edge, int H, const float* mpre, const float
   GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_tail: H=%d not in (0, %d]", H, 32 * MAXC);
   GEOLDM_REQUIRE(gate ? (agg != nullptr && (!attention || (w && bw))) : (sc != nullptr && w != nullptr), "train_edge_tail: bad arguments%s", "");
   if (n_edge == 0) return 0;
-  edge_tail_fwd_kernel<<<train_grid(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, attention || !gate ? w : nullptr, bw, gate,
+  edge_tail_fwd_kernel<<<train_grid_bwd(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, attention || !gate ? w : nullptr, bw, gate,
                                                                             attention, edge_i, 1.0f / div, agg, sc);
   GEOLDM_CHECK_LAUNCH("edge_tail_fwd_kernel");
   return 0;
 }
 int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
                                int gate, int attention, const int* edge_i, float div, const float* dagg, const float* dsc,
-                               float* dmpre, float* db2, float* dw, float* dbw, void* stream) {
+                               float* dmpre, float* db2, float* dw, float* dbw, double* dbw_scratch, void* stream) {
   using namespace geoldm;
   GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_tail: H=%d not in (0, %d]", H, 32 * MAXC);
   if (n_edge == 0) return 0;
   const bool use_w = attention || !gate;
   edge_tail_bwd_kernel<<<train_grid_bwd(n_edge), 32 * TRAIN_WARPS, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, use_w ? w : nullptr, bw, gate, attention,
                                                                             edge_i, 1.0f / div, dagg, dsc, dmpre, db2,
-                                                                            use_w ? dw : nullptr, (gate && attention) ? dbw : nullptr);
+                                                                            use_w ? dw : nullptr, (gate && attention) ? dbw : nullptr,
+                                                                            dbw_scratch);
   GEOLDM_CHECK_LAUNCH("edge_tail_bwd_kernel");
   return 0;
 }
 }
+
+extern "C" int geoldm_train_bwd_blocks(int n_edge) { return geoldm::train_grid_bwd(n_edge); }
 
 extern "C" int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
                               void* stream) {

@@ -194,11 +194,15 @@ class _EdgeTailFn(torch.autograd.Function):
         db2 = torch.zeros_like(b2)
         dw = None if w is None else torch.zeros_like(w)
         dbw = None if bw is None else torch.zeros_like(bw)
+        # scratch of the deterministic double-precision reduction of the attention-bias gradient (zeroed, left zeroed)
+        scratch = None
+        if dbw is not None and gate and attention:
+            scratch = torch.zeros(_lib.lib().geoldm_train_bwd_blocks(E) + 1, dtype=torch.float64, device=mpre.device)
         _lib.check(_lib.lib().geoldm_train_edge_tail_bwd(E, H, _lib.ptr(mpre), _lib.ptr(b2), _lib.ptr(w), _lib.ptr(bw),
                                                          int(gate), int(attention), _lib.ptr(ei32), div,
                                                          _lib.ptr(dout) if gate else None, None if gate else _lib.ptr(dout),
                                                          _lib.ptr(dmpre), _lib.ptr(db2), _lib.ptr(dw), _lib.ptr(dbw),
-                                                         _stream(mpre)), "train_edge_tail_bwd")
+                                                         _lib.ptr(scratch), _stream(mpre)), "train_edge_tail_bwd")
         if w is not None and not (attention or not gate):
             dw = None
         return dmpre, db2, dw, dbw, None, None, None, None, None

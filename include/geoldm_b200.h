@@ -241,7 +241,12 @@ int geoldm_train_edge_tail_fwd(int n_edge, int H, const float* mpre, const float
                                void* stream);
 int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
                                int gate, int attention, const int* edge_i, float div, const float* dagg, const float* dsc,
-                               float* dmpre, float* db2, float* dw, float* dbw, void* stream);
+                               float* dmpre, float* db2, float* dw, float* dbw,
+                               double* dbw_scratch, /* [geoldm_train_bwd_blocks(n_edge) + 1] doubles, ZEROED once (the kernel leaves it zeroed), or
+                                                     * NULL: dbw is accumulated with float atomics in arrival order (not reproducible) */
+                               void* stream);
+/* number of thread blocks the backward edge kernels launch for n_edge edges (sizes dbw_scratch) */
+int geoldm_train_bwd_blocks(int n_edge);
 /* ---- evaluation side: bond-order stability of a ragged batch of molecules.
  * Replaces the Python double loop of qm9/analyze.py:209-245 (check_stability) + qm9/bond_analyze.py:101-146.
  * x [N][3] fp32, atom_type [N] in [0, n_types), mol_off [n_mol+1]; thr [3][n_types][n_types] = single/double/triple

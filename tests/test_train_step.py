@@ -13,7 +13,16 @@ from tests.helpers import build_cuda_model, load_golden
 
 LOSS_TOL = 1e-5
 GRAD_TOL = 3e-5        # measured 1e-6 (small cases) .. 1.3e-5 (nf=192, 9 blocks, after subtracting the reference's own fp32 noise)
-GRAD_TOL64 = 3e-5      # vs the float64 run of the reference (full-size case)
+# vs the float64 run of the reference (full-size case), two classes of tensors:
+#  * more than one element: 1.5e-5 (measured over 30 runs on B200: 2e-6 .. 7e-6; the rest of the margin is for the order of
+#    the fp32 atomics in the scatter kernels, which differs from run to run);
+#  * single-element tensors - the attention biases, each a CANCELLING sum of ~20 k signed per-edge terms that leaves a
+#    5e-6-sized value: 5e-5.  Their own reduction is deterministic and in double (train.cu, dbw_scratch), but their inputs
+#    carry the 1e-7 order-of-atomics noise of the upstream scatter adds, which the cancellation amplifies: measured 3e-6 ..
+#    2.3e-5 over 30 runs (3.1e-5 before the deterministic reduction).  The reference's own fp32 run is 3.6e-5 away from its
+#    fp64 run on one of them.
+GRAD_TOL64 = 1.5e-5
+GRAD_TOL64_SCALAR = 5e-5
 
 
 def _rel(a, b):
@@ -74,7 +83,8 @@ def _check_case(name, device, monkeypatch=None):
         # rounding noise (up to 3.6e-5 on a 5e-6-sized attention-bias gradient that is a cancelling sum over all
         # edges), so each tensor is gated by  err(ours, ref32) <= GRAD_TOL + err(ref32, ref64)  and
         # err(ours, ref64) <= GRAD_TOL64.
-        worst64, floor_at_worst = 0.0, 0.0
+        worst64, floor_at_worst, wname64 = 0.0, 0.0, None
+        worst64_scalar = 0.0
         for i, n in enumerate(names):
             gp = grads[n]
             head = gp.flatten()[:256].double().cpu()
@@ -87,12 +97,16 @@ def _check_case(name, device, monkeypatch=None):
             e64 = err(A["gmax64"][i], A["gl264"][i], A["ghead64"][i])
             floor = max(abs(float(A["gmax"][i]) - float(A["gmax64"][i])) / float(A["gmax64"][i]),
                         float((A["ghead"][i].double() - A["ghead64"][i].double()).abs().max()) / float(A["gmax64"][i]))
-            worst64 = max(worst64, e64)
+            if gp.numel() == 1:
+                worst64_scalar = max(worst64_scalar, e64)
+            elif e64 > worst64:
+                worst64, wname64 = e64, n
             if e32 - floor > worst - floor_at_worst:
                 worst, wname, floor_at_worst = e32, n, floor
-        print(f"[train] {name}: worst grad vs fp64 reference {worst64:.2e}; vs fp32 reference {worst:.2e} "
+        print(f"[train] {name}: worst grad vs fp64 reference {worst64:.2e} ({wname64}), single-element tensors "
+              f"{worst64_scalar:.2e}; vs fp32 reference {worst:.2e} "
               f"(reference's own fp32 noise there {floor_at_worst:.2e})")
-        assert worst64 < GRAD_TOL64
+        assert worst64 < GRAD_TOL64 and worst64_scalar < GRAD_TOL64_SCALAR
         worst = max(0.0, worst - floor_at_worst)
     else:
         ref = {k[2:]: v for k, v in A.items() if k.startswith("g.")}
