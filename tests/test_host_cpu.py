@@ -100,6 +100,12 @@ def test_balance_shards():
     assert sorted(np.concatenate(shards).tolist()) == list(range(1000))
     loads = [int((n[s] * (n[s] - 1)).sum()) for s in shards]
     assert max(loads) / min(loads) < 1.01
+    n = rng.integers(3, 30, size=5000)                       # large jobs: the vectorised deal
+    shards = balance_shards(n, 8)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(5000))
+    assert all(np.all(np.diff(s) > 0) for s in shards)
+    loads = [int((n[s] * (n[s] - 1)).sum()) for s in shards]
+    assert max(loads) / min(loads) < 1.005
 
 
 def test_philox_known_answers():
