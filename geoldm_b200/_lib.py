@@ -80,6 +80,7 @@ _SIGS = {
                                    fp, C.c_int, fp]),
     "geoldm_tc_selftest": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_int, fp, fp, fp]),
     "geoldm_gemm_tn": (C.c_int, [fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp]),
+    "geoldm_gemm_tn_bias": (C.c_int, [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, fp]),
     "geoldm_train_edge_act_fwd": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, fp, fp, fp, fp, fp, fp]),
     "geoldm_train_edge_act_bwd": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp]),
     "geoldm_train_edge_tail_fwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp]),

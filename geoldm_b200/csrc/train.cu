@@ -10,7 +10,7 @@ constexpr int TN_BN = 64, TN_BK = 64, TN_BM = 16, TN_T = 256;
 
 __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b,
                                                       int ldb, float* __restrict__ c, int ldc, int m, int n, int k,
-                                                      int m_per_split) {
+                                                      int m_per_split, float* __restrict__ colsum) {
   __shared__ __align__(16) float As[2][TN_BM][TN_BN];
   __shared__ __align__(16) float Bs[2][TN_BM][TN_BK];
   const int t = threadIdx.x;
@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
   // global -> registers (issued before the FMAs of the current slab) -> shared (after them): the L2 latency of the next
   // 16-row slab is hidden behind 256 FMAs per thread instead of being exposed at every slab
   float4 va, vb;
+  // bias gradient (colsum[n] += sum_m A[m][n], optional): the k0 == 0 blocks add up the A values they stage anyway, one
+  // float4 per thread and slab, and combine the 16 row phases through shared memory at the end
+  const bool do_colsum = colsum != nullptr && blockIdx.x == 0;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   auto g_load = [&](int mrow) {
     va = make_float4(0.f, 0.f, 0.f, 0.f); vb = va;
     const int mm = mrow + lr;
@@ -42,6 +46,7 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
     }
   };
   auto s_store = [&](int buf) {
+    cs.x += va.x; cs.y += va.y; cs.z += va.z; cs.w += va.w;
     *reinterpret_cast<float4*>(&As[buf][lr][lc]) = va;
     *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = vb;
   };
@@ -76,6 +81,17 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
       if (kk < k) atomicAdd(c + (size_t)nn * ldc + kk, acc[i][j]);
     }
   }
+  if (do_colsum) {                                   // block-uniform
+    __syncthreads();                                 // (the loop ends with a barrier; kept explicit for the reuse of As)
+    *reinterpret_cast<float4*>(&As[0][lr][lc]) = cs;
+    __syncthreads();
+    if (t < TN_BN && n0 + t < n) {
+      float v = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < TN_BM; ++rr) v += As[0][rr][t];
+      atomicAdd(colsum + n0 + t, v);
+    }
+  }
 }
 }  // namespace
 }  // namespace geoldm
@@ -90,7 +106,21 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 namespace geoldm {
 namespace {
-constexpr int MAXC = 8;   // columns per lane: H <= 256
+// lane -> columns: 16-byte groups, lane owns columns 128 g + 4 lane .. + 3 of group g (H <= 256, H % 4 == 0): every row
+// access is one float4 per lane (a warp covers 512 contiguous bytes) and the scatter-adds are 16-byte vector reductions
+// (red.global.add.v4.f32: a quarter of the L2 reduction operations of the scalar form, which bounded edge_act_bwd)
+constexpr int MAXG = 2;
+
+__device__ __forceinline__ void ld4(const float* p, float (&o)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* p, const float (&o)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void red4(float* p, const float (&o)[4]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+}
 
 // ex2.approx (2 ulp) + correctly rounded division: with rcp.approx as well the worst config-5 gradient tensor moved from
 // 6e-6 to 1.03e-5 of the fp64 reference run (north_star's tolerance is 1e-5), with accurate expf the kernels are 10 % slower
@@ -112,14 +142,19 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-// Per-column partial sums of the 8 warps of a block (lane owns columns lane + 32 k) -> shared memory -> ONE atomicAdd per
-// column and block.  Every warp adding its own partials to the same [H] global vector serialises in the L2 atomic unit
-// (thousands of reductions onto the same few 128-byte lines): measured 80-93 us per launch before, mostly that.
+// Per-column partial sums of the 8 warps of a block -> shared memory -> ONE atomicAdd per column and block.  Every warp
+// adding its own partials to the same [H] global vector serialises in the L2 atomic unit (thousands of reductions onto
+// the same few 128-byte lines): measured 80-93 us per launch before, mostly that.
 constexpr int TRAIN_WARPS = 8;
-__device__ __forceinline__ void block_column_add(float (*red)[32 * MAXC], const float (&acc)[MAXC], int H, float* __restrict__ out) {
+// backward kernels: few fat blocks (every block ends with one reduction per column into the weight gradients), all resident
+// at once: 3 blocks of 256 threads per SM at <= 80 registers (4 per SM spill, 2 per SM leave half of the warp slots empty)
+#ifndef GEOLDM_TRAIN_BWD_BLOCKS_PER_SM
+#define GEOLDM_TRAIN_BWD_BLOCKS_PER_SM 3
+#endif
+__device__ __forceinline__ void block_column_add(float (*red)[128 * MAXG], const float (&acc)[MAXG][4], int H, float* __restrict__ out) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) red[w][lane + 32 * k] = acc[k];
+  for (int g = 0; g < MAXG; ++g) st4(&red[w][128 * g + 4 * lane], acc[g]);
   __syncthreads();
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float v = 0.f;
@@ -135,39 +170,62 @@ __global__ void edge_act_fwd_kernel(int E, int H, const float* __restrict__ pq, 
                                     const int* __restrict__ ei, const int* __restrict__ ej, float* __restrict__ a) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  float wr[MAXG][4], wd[MAXG][4];
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    const int c0 = 128 * g + 4 * lane;
+    if (c0 < H) { ld4(w_rd + c0, wr[g]); ld4(w_rd + H + c0, wd[g]); }
+  }
   for (int e = warp; e < E; e += nwarp) {
     const float* P = pq + (size_t)ei[e] * pq_ld;
     const float* Q = pq + (size_t)ej[e] * pq_ld + H;
     const float re = r[e], de = d0[e];
-    for (int c = lane; c < H; c += 32) {
-      const float z = P[c] + Q[c] + re * w_rd[c] + de * w_rd[H + c];
-      a[(size_t)e * H + c] = z * sigm(z);
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+      if (c0 < H) {
+        float p[4], q[4], o[4];
+        ld4(P + c0, p); ld4(Q + c0, q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float z = p[t] + q[t] + re * wr[g][t] + de * wd[g][t];
+          o[t] = z * sigm(z);
+        }
+        st4(a + (size_t)e * H + c0, o);
+      }
     }
   }
 }
 
-__global__ void edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, int pq_ld, const float* __restrict__ r,
+__global__ void __launch_bounds__(32 * TRAIN_WARPS, GEOLDM_TRAIN_BWD_BLOCKS_PER_SM) edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, int pq_ld, const float* __restrict__ r,
                                     const float* __restrict__ d0, const float* __restrict__ w_rd,
                                     const int* __restrict__ ei, const int* __restrict__ ej, const float* __restrict__ da,
                                     float* __restrict__ dpq, float* __restrict__ dr, float* __restrict__ dd0,
                                     float* __restrict__ dw_rd) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-  float acc_r[MAXC], acc_d[MAXC], acc_p[MAXC];
+  float acc_r[MAXG][4], acc_d[MAXG][4], acc_p[MAXG][4], wr[MAXG][4], wd[MAXG][4];
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) acc_r[k] = acc_d[k] = acc_p[k] = 0.f;
+  for (int g = 0; g < MAXG; ++g) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc_r[g][t] = acc_d[g][t] = acc_p[g][t] = wr[g][t] = wd[g][t] = 0.f;
+    const int c0 = 128 * g + 4 * lane;
+    if (c0 < H) { ld4(w_rd + c0, wr[g]); ld4(w_rd + H + c0, wd[g]); }
+  }
   // a warp owns a CONTIGUOUS range of edge rows: rows are sorted by receiver, so the receiver-side gradient dP_i is summed
-  // in registers over the run (fixed order) and leaves as one atomic per (run piece, column) instead of one per edge
+  // in registers over the run (fixed order) and leaves as one vector reduction per (run piece, 4 columns) instead of one
+  // per edge; the sender-side gradient dQ_j is one vector reduction per (edge, 4 columns)
   const int per = (E + nwarp - 1) / nwarp;
   const int e_begin = min(E, warp * per), e_end = min(E, e_begin + per);
   int cur_i = -1;
   auto flush_p = [&]() {
     if (cur_i < 0) return;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      if (c < H) atomicAdd(dpq + (size_t)cur_i * pq_ld + c, acc_p[k]);
-      acc_p[k] = 0.f;
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+      if (c0 < H) red4(dpq + (size_t)cur_i * pq_ld + c0, acc_p[g]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc_p[g][t] = 0.f;
     }
   };
   for (int e = e_begin; e < e_end; ++e) {
@@ -178,24 +236,29 @@ __global__ void edge_act_bwd_kernel(int E, int H, const float* __restrict__ pq, 
     const float re = r[e], de = d0[e];
     float sr = 0.f, sd = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      if (c < H) {
-        const float wr = w_rd[c], wd = w_rd[H + c];
-        const float z = P[c] + Q[c] + re * wr + de * wd;
-        const float s = sigm(z);
-        const float g = da[(size_t)e * H + c] * (s * (1.0f + z * (1.0f - s)));     // d SiLU / dz
-        acc_p[k] += g;
-        atomicAdd(dpq + (size_t)j * pq_ld + H + c, g);
-        sr += g * wr; sd += g * wd;
-        acc_r[k] += g * re; acc_d[k] += g * de;
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+      if (c0 < H) {
+        float p[4], q[4], u[4], gq[4];
+        ld4(P + c0, p); ld4(Q + c0, q); ld4(da + (size_t)e * H + c0, u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float z = p[t] + q[t] + re * wr[g][t] + de * wd[g][t];
+          const float s = sigm(z);
+          const float gv = u[t] * (s * (1.0f + z * (1.0f - s)));     // d SiLU / dz
+          gq[t] = gv;
+          acc_p[g][t] += gv;
+          sr += gv * wr[g][t]; sd += gv * wd[g][t];
+          acc_r[g][t] += gv * re; acc_d[g][t] += gv * de;
+        }
+        red4(dpq + (size_t)j * pq_ld + H + c0, gq);
       }
     }
     sr = warp_sum_f(sr); sd = warp_sum_f(sd);
     if (lane == 0) { dr[e] = sr; dd0[e] = sd; }
   }
   flush_p();
-  __shared__ float red[TRAIN_WARPS][32 * MAXC];
+  __shared__ __align__(16) float red[TRAIN_WARPS][128 * MAXG];
   block_column_add(red, acc_r, H, dw_rd);
   block_column_add(red, acc_d, H, dw_rd + H);
 }
@@ -207,112 +270,144 @@ __global__ void edge_tail_fwd_kernel(int E, int H, const float* __restrict__ mpr
                                      float* __restrict__ sc) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-  // contiguous edge range per warp: the messages of a receiver run are summed in registers (fixed order), one atomic per
-  // (run piece, column)
+  // contiguous edge range per warp: the messages of a receiver run are summed in registers (fixed order), one vector
+  // reduction per (run piece, 4 columns)
   const int per = (E + nwarp - 1) / nwarp;
   const int e_begin = min(E, warp * per), e_end = min(E, e_begin + per);
   int cur_i = -1;
-  float acc_a[MAXC];
+  float acc_a[MAXG][4], bb[MAXG][4], ww[MAXG][4];
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) acc_a[k] = 0.f;
+  for (int g = 0; g < MAXG; ++g) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc_a[g][t] = bb[g][t] = ww[g][t] = 0.f;
+    const int c0 = 128 * g + 4 * lane;
+    if (c0 < H) { ld4(b2 + c0, bb[g]); if (w) ld4(w + c0, ww[g]); }
+  }
   auto flush_a = [&]() {
     if (cur_i < 0) return;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      if (c < H) atomicAdd(agg + (size_t)cur_i * H + c, acc_a[k]);
-      acc_a[k] = 0.f;
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+      if (c0 < H) red4(agg + (size_t)cur_i * H + c0, acc_a[g]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc_a[g][t] = 0.f;
     }
   };
   for (int e = e_begin; e < e_end; ++e) {
-    float m[MAXC];
+    float m[MAXG][4];
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      m[k] = 0.f;
-      if (c < H) {
-        const float z = mpre[(size_t)e * H + c] + b2[c];
-        m[k] = z * sigm(z);
-        if (w) dot += m[k] * w[c];
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) m[g][t] = 0.f;
+      if (c0 < H) {
+        float v[4];
+        ld4(mpre + (size_t)e * H + c0, v);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float z = v[t] + bb[g][t];
+          m[g][t] = z * sigm(z);
+          dot += m[g][t] * ww[g][t];
+        }
       }
     }
     dot = warp_sum_f(dot);
     if (!gate) { if (lane == 0) sc[e] = dot; continue; }
-    const float g = attention ? sigm(dot + bw[0]) : 1.0f;
+    const float gt = attention ? sigm(dot + bw[0]) : 1.0f;
     const int i = ei[e];
     if (i != cur_i) { flush_a(); cur_i = i; }
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) acc_a[k] += m[k] * g * inv_div;
+    for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc_a[g][t] += m[g][t] * gt * inv_div;
   }
   if (gate) flush_a();
 }
 
-__global__ void edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpre, const float* __restrict__ b2,
+__global__ void __launch_bounds__(32 * TRAIN_WARPS, GEOLDM_TRAIN_BWD_BLOCKS_PER_SM) edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpre, const float* __restrict__ b2,
                                      const float* __restrict__ w, const float* __restrict__ bw, int gate, int attention,
                                      const int* __restrict__ ei, float inv_div, const float* __restrict__ dagg,
                                      const float* __restrict__ dsc, float* __restrict__ dmpre, float* __restrict__ db2,
                                      float* __restrict__ dw, float* __restrict__ dbw, double* __restrict__ bw_scratch) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-  float acc_b[MAXC], acc_w[MAXC];
+  float acc_b[MAXG][4], acc_w[MAXG][4], bb[MAXG][4], ww[MAXG][4];
   double acc_bw = 0.0;      // attention-bias gradient: a cancelling sum over ALL edges, kept in double and summed in a fixed order
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) acc_b[k] = acc_w[k] = 0.f;
+  for (int g = 0; g < MAXG; ++g) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc_b[g][t] = acc_w[g][t] = bb[g][t] = ww[g][t] = 0.f;
+    const int c0 = 128 * g + 4 * lane;
+    if (c0 < H) { ld4(b2 + c0, bb[g]); if (w) ld4(w + c0, ww[g]); }
+  }
   for (int e = warp; e < E; e += nwarp) {
-    float m[MAXC], dz[MAXC], de[MAXC];
+    float m[MAXG][4], dz[MAXG][4], de[MAXG][4];
     float dot = 0.f, dg = 0.f;
     const float* din = gate ? dagg + (size_t)ei[e] * H : nullptr;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      m[k] = dz[k] = de[k] = 0.f;
-      if (c < H) {
-        const float z = mpre[(size_t)e * H + c] + b2[c];
-        const float s = sigm(z);
-        m[k] = z * s;
-        dz[k] = s * (1.0f + z * (1.0f - s));
-        if (w) dot += m[k] * w[c];
-        if (gate) { de[k] = din[c] * inv_div; dg += de[k] * m[k]; }
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) m[g][t] = dz[g][t] = de[g][t] = 0.f;
+      if (c0 < H) {
+        float v[4], d4[4] = {0.f, 0.f, 0.f, 0.f};
+        ld4(mpre + (size_t)e * H + c0, v);
+        if (gate) ld4(din + c0, d4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float z = v[t] + bb[g][t];
+          const float s = sigm(z);
+          m[g][t] = z * s;
+          dz[g][t] = s * (1.0f + z * (1.0f - s));
+          dot += m[g][t] * ww[g][t];
+          if (gate) { de[g][t] = d4[t] * inv_div; dg += de[g][t] * m[g][t]; }
+        }
       }
     }
     dot = warp_sum_f(dot);
-    float g = 1.0f, ds;
+    float gt = 1.0f, ds;
     if (gate) {
       dg = warp_sum_f(dg);
       ds = 0.f;
-      if (attention) { g = sigm(dot + bw[0]); ds = dg * g * (1.0f - g); }
+      if (attention) { gt = sigm(dot + bw[0]); ds = dg * gt * (1.0f - gt); }
     } else {
       ds = dsc[e];
     }
     if (lane == 0 && dbw) acc_bw += (double)ds;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      const int c = lane + 32 * k;
-      if (c < H) {
-        float dm = gate ? de[k] * g : 0.f;
-        if (w) { dm += ds * w[c]; acc_w[k] += ds * m[k]; }
-        const float o = dm * dz[k];
-        dmpre[(size_t)e * H + c] = o;
-        acc_b[k] += o;
+    for (int g = 0; g < MAXG; ++g) {
+      const int c0 = 128 * g + 4 * lane;
+      if (c0 < H) {
+        float o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float dm = gate ? de[g][t] * gt : 0.f;
+          if (w) { dm += ds * ww[g][t]; acc_w[g][t] += ds * m[g][t]; }
+          o[t] = dm * dz[g][t];
+          acc_b[g][t] += o[t];
+        }
+        st4(dmpre + (size_t)e * H + c0, o);
       }
     }
   }
-  __shared__ float red[TRAIN_WARPS][32 * MAXC];
+  __shared__ __align__(16) float red[TRAIN_WARPS][128 * MAXG];
   block_column_add(red, acc_b, H, db2);
   if (dw) block_column_add(red, acc_w, H, dw);
   if (dbw) {
-    // block partial (double, fixed warp order) -> scratch[block]; the LAST block to finish adds all partials in block order
-    // and accumulates the total into dbw: deterministic and accurate to double rounding.  (Float atomics in arrival order
-    // made this 5e-6-sized scalar wander by up to 3e-5 relative from run to run.)
-    __shared__ double red_bw[TRAIN_WARPS];
+    // block partial (double, fixed warp order) -> scratch[block]; the LAST block to finish adds all partials in a fixed
+    // order (strided per thread, then a shared-memory tree: the whole block takes part, a single thread walking 592
+    // dependent L2 loads cost tens of microseconds per launch) and accumulates the total into dbw: deterministic and
+    // accurate to double rounding.  (Float atomics in arrival order made this 5e-6-sized scalar wander by up to 3e-5
+    // relative from run to run.)
+    __shared__ double red_bw[32 * TRAIN_WARPS];
     __shared__ bool is_last;
     if (lane == 0) red_bw[threadIdx.x >> 5] = acc_bw;
     __syncthreads();
     if (threadIdx.x == 0) {
       double v = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < TRAIN_WARPS; ++ww) v += red_bw[ww];
+      for (int k = 0; k < TRAIN_WARPS; ++k) v += red_bw[k];
       if (bw_scratch) {
         bw_scratch[blockIdx.x] = v;
         __threadfence();
@@ -324,25 +419,31 @@ __global__ void edge_tail_bwd_kernel(int E, int H, const float* __restrict__ mpr
       }
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {
       __threadfence();
-      double total = 0.0;
-      for (unsigned bb = 0; bb < gridDim.x; ++bb) total += reinterpret_cast<volatile double*>(bw_scratch)[bb];
-      dbw[0] += (float)total;
-      *reinterpret_cast<unsigned*>(bw_scratch + gridDim.x) = 0u;        // the scratch is reusable
+      double v = 0.0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += reinterpret_cast<volatile double*>(bw_scratch)[b];
+      red_bw[threadIdx.x] = v;
+      __syncthreads();
+      for (int s = (32 * TRAIN_WARPS) / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red_bw[threadIdx.x] += red_bw[threadIdx.x + s];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        dbw[0] += (float)red_bw[0];
+        *reinterpret_cast<unsigned*>(bw_scratch + gridDim.x) = 0u;        // the scratch is reusable
+      }
     }
   }
 }
 
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int train_grid(int E) { int b = (E + 7) / 8; return b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b); }
-// backward kernels: few fat blocks (every block ends with one reduction per column into the weight gradients)
-#ifndef GEOLDM_TRAIN_BWD_BLOCKS_PER_SM
-#define GEOLDM_TRAIN_BWD_BLOCKS_PER_SM 4
-#endif
-inline int train_grid_bwd(int E) {
+inline int train_grid_fat(int E, int per_sm) {
   int b = (E + 7) / 8;
-  return b < 1 ? 1 : (b > 148 * GEOLDM_TRAIN_BWD_BLOCKS_PER_SM ? 148 * GEOLDM_TRAIN_BWD_BLOCKS_PER_SM : b);
+  return b < 1 ? 1 : (b > 148 * per_sm ? 148 * per_sm : b);
 }
+inline int train_grid_bwd(int E) { return train_grid_fat(E, GEOLDM_TRAIN_BWD_BLOCKS_PER_SM); }
 }  // namespace
 }  // namespace geoldm
 
@@ -350,7 +451,8 @@ extern "C" {
 int geoldm_train_edge_act_fwd(int n_edge, int H, const float* pq, int pq_ld, const float* r, const float* d0,
                               const float* w_rd, const int* edge_i, const int* edge_j, float* a, void* stream) {
   using namespace geoldm;
-  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_act: H=%d not in (0, %d]", H, 32 * MAXC);
+  GEOLDM_REQUIRE(H > 0 && H <= 128 * MAXG && H % 4 == 0, "train_edge_act: H=%d not a multiple of 4 in (0, %d]", H, 128 * MAXG);
+  GEOLDM_REQUIRE(pq_ld % 4 == 0 && al16(pq) && al16(w_rd) && al16(a), "train_edge_act_fwd: pq / w_rd / a must be 16-byte aligned, pq_ld=%d a multiple of 4", pq_ld);
   if (n_edge == 0) return 0;
   edge_act_fwd_kernel<<<train_grid(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, pq, pq_ld, r, d0, w_rd, edge_i, edge_j, a);
   GEOLDM_CHECK_LAUNCH("edge_act_fwd_kernel");
@@ -360,7 +462,8 @@ int geoldm_train_edge_act_bwd(int n_edge, int H, const float* pq, int pq_ld, con
                               const float* w_rd, const int* edge_i, const int* edge_j, const float* da, float* dpq,
                               float* dr, float* dd0, float* dw_rd, void* stream) {
   using namespace geoldm;
-  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_act: H=%d not in (0, %d]", H, 32 * MAXC);
+  GEOLDM_REQUIRE(H > 0 && H <= 128 * MAXG && H % 4 == 0, "train_edge_act: H=%d not a multiple of 4 in (0, %d]", H, 128 * MAXG);
+  GEOLDM_REQUIRE(pq_ld % 4 == 0 && al16(pq) && al16(w_rd) && al16(da) && al16(dpq), "train_edge_act_bwd: pq / w_rd / da / dpq must be 16-byte aligned, pq_ld=%d a multiple of 4", pq_ld);
   if (n_edge == 0) return 0;
   edge_act_bwd_kernel<<<train_grid_bwd(n_edge), 32 * TRAIN_WARPS, 0, (cudaStream_t)stream>>>(n_edge, H, pq, pq_ld, r, d0, w_rd, edge_i, edge_j, da,
                                                                            dpq, dr, dd0, dw_rd);
@@ -371,10 +474,11 @@ int geoldm_train_edge_tail_fwd(int n_edge, int H, const float* mpre, const float
                                int gate, int attention, const int* edge_i, float div, float* agg, float* sc,
                                void* stream) {
   using namespace geoldm;
-  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_tail: H=%d not in (0, %d]", H, 32 * MAXC);
+  GEOLDM_REQUIRE(H > 0 && H <= 128 * MAXG && H % 4 == 0, "train_edge_tail: H=%d not a multiple of 4 in (0, %d]", H, 128 * MAXG);
   GEOLDM_REQUIRE(gate ? (agg != nullptr && (!attention || (w && bw))) : (sc != nullptr && w != nullptr), "train_edge_tail: bad arguments%s", "");
+  GEOLDM_REQUIRE(al16(mpre) && al16(b2) && al16(w) && al16(agg), "train_edge_tail_fwd: mpre / b2 / w / agg must be 16-byte aligned%s", "");
   if (n_edge == 0) return 0;
-  edge_tail_fwd_kernel<<<train_grid_bwd(n_edge), 256, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, attention || !gate ? w : nullptr, bw, gate,
+  edge_tail_fwd_kernel<<<train_grid_fat(n_edge, 4), 256, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, attention || !gate ? w : nullptr, bw, gate,
                                                                             attention, edge_i, 1.0f / div, agg, sc);
   GEOLDM_CHECK_LAUNCH("edge_tail_fwd_kernel");
   return 0;
@@ -383,7 +487,8 @@ int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float
                                int gate, int attention, const int* edge_i, float div, const float* dagg, const float* dsc,
                                float* dmpre, float* db2, float* dw, float* dbw, double* dbw_scratch, void* stream) {
   using namespace geoldm;
-  GEOLDM_REQUIRE(H > 0 && H <= 32 * MAXC, "train_edge_tail: H=%d not in (0, %d]", H, 32 * MAXC);
+  GEOLDM_REQUIRE(H > 0 && H <= 128 * MAXG && H % 4 == 0, "train_edge_tail: H=%d not a multiple of 4 in (0, %d]", H, 128 * MAXG);
+  GEOLDM_REQUIRE(al16(mpre) && al16(b2) && al16(w) && al16(dagg) && al16(dmpre), "train_edge_tail_bwd: mpre / b2 / w / dagg / dmpre must be 16-byte aligned%s", "");
   if (n_edge == 0) return 0;
   const bool use_w = attention || !gate;
   edge_tail_bwd_kernel<<<train_grid_bwd(n_edge), 32 * TRAIN_WARPS, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, use_w ? w : nullptr, bw, gate, attention,
@@ -397,8 +502,8 @@ int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float
 
 extern "C" int geoldm_train_bwd_blocks(int n_edge) { return geoldm::train_grid_bwd(n_edge); }
 
-extern "C" int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
-                              void* stream) {
+extern "C" int geoldm_gemm_tn_bias(const float* a, int lda, const float* b, int ldb, float* c, int ldc, float* colsum,
+                                   int m, int n, int k, void* stream) {
   using namespace geoldm;
   GEOLDM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "gemm_tn: lda=%d ldb=%d must be multiples of 4", lda, ldb);
   if (m == 0 || n == 0 || k == 0) return 0;
@@ -410,7 +515,11 @@ extern "C" int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, 
   int m_per_split = ((m + splits - 1) / splits + TN_BM - 1) / TN_BM * TN_BM;
   splits = (m + m_per_split - 1) / m_per_split;
   dim3 grid((k + TN_BK - 1) / TN_BK, (n + TN_BN - 1) / TN_BN, splits);
-  gemm_tn_kernel<<<grid, TN_T, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, c, ldc, m, n, k, m_per_split);
+  gemm_tn_kernel<<<grid, TN_T, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, c, ldc, m, n, k, m_per_split, colsum);
   GEOLDM_CHECK_LAUNCH("gemm_tn_kernel");
   return 0;
+}
+extern "C" int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
+                              void* stream) {
+  return geoldm_gemm_tn_bias(a, lda, b, ldb, c, ldc, nullptr, m, n, k, stream);
 }

@@ -99,11 +99,16 @@ class _LinearFn(torch.autograd.Function):
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
             _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
                                        _stream(x)), "geoldm_linear(dX)")
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros(N, K, device=x.device, dtype=torch.float32)
-            _lib.check(L.geoldm_gemm_tn(_lib.ptr(dy), N, _lib.ptr(x), K, _lib.ptr(dw), K, M, N, K, _stream(x)),
-                       "geoldm_gemm_tn(dW)")
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            # dW and the bias gradient from ONE pass over dY (geoldm_gemm_tn_bias: the k0 == 0 blocks also add up the dY
+            # columns), both carved from one zero-filled allocation: no separate column-sum launch, one fill instead of two
+            buf = torch.zeros(N * K + (N if want_db else 0), device=x.device, dtype=torch.float32)
+            dw = buf[:N * K].view(N, K)
+            db = buf[N * K:] if want_db else None
+            _lib.check(L.geoldm_gemm_tn_bias(_lib.ptr(dy), N, _lib.ptr(x), K, _lib.ptr(dw), K, _lib.ptr(db), M, N, K,
+                                             _stream(x)), "geoldm_gemm_tn_bias(dW, db)")
+        elif want_db:
             db = dy.sum(0)
         return dx, dw, db
 
@@ -154,8 +159,9 @@ class _EdgeActFn(torch.autograd.Function):
         pq, r, d0, w_rd, ei32, ej32 = ctx.saved_tensors
         E, H = ei32.numel(), w_rd.shape[1]
         da = da.contiguous()
-        dpq = torch.zeros_like(pq)
-        dw = torch.zeros_like(w_rd)
+        buf = torch.zeros(pq.numel() + w_rd.numel(), device=pq.device, dtype=torch.float32)   # one fill for both
+        dpq = buf[:pq.numel()].view_as(pq)
+        dw = buf[pq.numel():].view_as(w_rd)
         dr = torch.empty(E, device=pq.device, dtype=torch.float32)
         dd0 = torch.empty(E, device=pq.device, dtype=torch.float32)
         _lib.check(_lib.lib().geoldm_train_edge_act_bwd(E, H, _lib.ptr(pq), pq.shape[1], _lib.ptr(r), _lib.ptr(d0),
@@ -191,13 +197,16 @@ class _EdgeTailFn(torch.autograd.Function):
         E, H = mpre.shape
         dout = dout.contiguous()
         dmpre = torch.empty_like(mpre)
-        db2 = torch.zeros_like(b2)
-        dw = None if w is None else torch.zeros_like(w)
-        dbw = None if bw is None else torch.zeros_like(bw)
-        # scratch of the deterministic double-precision reduction of the attention-bias gradient (zeroed, left zeroed)
+        # db2 | dw | dbw carved from one zero-filled allocation (H is a multiple of 4: the vector pieces stay 16-byte aligned)
+        buf = torch.zeros(2 * H + 4, device=mpre.device, dtype=torch.float32)
+        db2 = buf[:H]
+        dw = None if w is None else buf[H:2 * H]
+        dbw = None if bw is None else buf[2 * H:2 * H + 1]
+        # scratch of the deterministic double-precision reduction of the attention-bias gradient: per-block partials + a
+        # counter the kernel leaves at zero, so ONE zero-initialised buffer per (device, grid) serves every launch
         scratch = None
         if dbw is not None and gate and attention:
-            scratch = torch.zeros(_lib.lib().geoldm_train_bwd_blocks(E) + 1, dtype=torch.float64, device=mpre.device)
+            scratch = _bw_scratch(mpre.device, _lib.lib().geoldm_train_bwd_blocks(E))
         _lib.check(_lib.lib().geoldm_train_edge_tail_bwd(E, H, _lib.ptr(mpre), _lib.ptr(b2), _lib.ptr(w), _lib.ptr(bw),
                                                          int(gate), int(attention), _lib.ptr(ei32), div,
                                                          _lib.ptr(dout) if gate else None, None if gate else _lib.ptr(dout),
@@ -206,6 +215,48 @@ class _EdgeTailFn(torch.autograd.Function):
         if w is not None and not (attention or not gate):
             dw = None
         return dmpre, db2, dw, dbw, None, None, None, None, None
+
+
+_BW_SCRATCH: dict = {}
+
+
+def _bw_scratch(dev, n_blocks):
+    """[n_blocks + 1] float64 partials + arrival counter of geoldm_train_edge_tail_bwd (launches on one stream run in order,
+    every launch overwrites all partials and resets the counter)."""
+    key = (dev.index, int(n_blocks))
+    t = _BW_SCRATCH.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.GeoldmError("the attention-bias scratch must exist before graph capture: run one eager step first")
+        t = _BW_SCRATCH[key] = torch.zeros(n_blocks + 1, dtype=torch.float64, device=dev)
+    return t
+
+
+class _SplitFirstFn(torch.autograd.Function):
+    """First edge layer weight [H, 2H + 2] / bias [H] -> the operands of its split form: projection weight [2H, H] (P rows,
+    then Q rows), projection bias [2H] (the layer bias on the P half, zero on the Q half) and the two distance columns as
+    [2, H].  One concatenation forward and one backward instead of autograd's slice / pad / accumulate chain per piece."""
+
+    @staticmethod
+    def forward(ctx, w1, b1):
+        H = w1.shape[0]
+        wpq = torch.cat([w1[:, :H], w1[:, H:2 * H]], dim=0)
+        bpq = torch.nn.functional.pad(b1, (0, H))
+        w_rd = w1[:, 2 * H:2 * H + 2].t().contiguous()
+        ctx.shape = tuple(w1.shape)
+        return wpq, bpq, w_rd
+
+    @staticmethod
+    def backward(ctx, dwpq, dbpq, dw_rd):
+        H, C = ctx.shape
+        ref = dwpq if dwpq is not None else dw_rd if dw_rd is not None else dbpq
+        z = lambda *s: torch.zeros(*s, device=ref.device, dtype=ref.dtype)
+        dwpq = z(2 * H, H) if dwpq is None else dwpq
+        dw_rd = z(2, H) if dw_rd is None else dw_rd
+        parts = [dwpq[:H], dwpq[H:], dw_rd.t()]
+        if C > 2 * H + 2:
+            parts.append(z(H, C - 2 * H - 2))
+        return torch.cat(parts, dim=1), (None if dbpq is None else dbpq[:H])
 
 
 def _fused_ok(h, H):
@@ -221,11 +272,10 @@ def _coord2diff(x, ei, ej, norm_constant):
 def _edge_pre(h, first, ei, ej, r, d0, H, e32):
     """First edge layer in split form: per-node projections + the two distance columns, then SiLU."""
     w1 = first.weight
-    wpq = torch.cat([w1[:, :H], w1[:, H:2 * H]], dim=0)                     # [2H, H]
-    bpq = torch.cat([first.bias, torch.zeros_like(first.bias)])
+    wpq, bpq, w_rd = _SplitFirstFn.apply(w1, first.bias)                    # [2H, H], [2H], [2, H]
     pq = linear(h, wpq, bpq)
     if _fused_ok(h, H):
-        return _EdgeActFn.apply(pq, r.reshape(-1), d0.reshape(-1), w1[:, 2 * H:2 * H + 2].t(), e32[0], e32[1])
+        return _EdgeActFn.apply(pq, r.reshape(-1), d0.reshape(-1), w_rd, e32[0], e32[1])
     pre1 = pq[:, :H].index_select(0, ei) + pq[:, H:].index_select(0, ej) + r * w1[:, 2 * H] + d0 * w1[:, 2 * H + 1]
     return F.silu(pre1)
 

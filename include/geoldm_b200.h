@@ -224,8 +224,12 @@ int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, con
  * zeroes C; lda/ldb multiples of 4).  Forward and input-gradient GEMMs of a Linear layer use geoldm_linear. */
 int geoldm_gemm_tn(const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
                    void* stream);
+/* the same GEMM with the bias gradient of the layer on the side: colsum[n] += sum_m A[m][n] (caller zeroes colsum; NULL:
+ * plain geoldm_gemm_tn).  One pass over dY instead of a separate column-sum launch per Linear layer. */
+int geoldm_gemm_tn_bias(const float* a, int lda, const float* b, int ldb, float* c, int ldc, float* colsum, int m, int n,
+                        int k, void* stream);
 /* Fused element-wise stages of the edge MLPs for the autograd path (forward + backward, everything recomputed from the
- * GEMM operands; one warp per edge; H <= 256).  pq [N][pq_ld] = P | Q projections; r, d0 [E] squared distances;
+ * GEMM operands; one warp per edge; H <= 256, H a multiple of 4, [.][H] operands 16-byte aligned).  pq [N][pq_ld] = P | Q projections; r, d0 [E] squared distances;
  * w_rd [2][H]; outputs of the backward kernels that are sums over edges (dpq, dw_rd, db2, dw, dbw) are ACCUMULATED with
  * atomics into caller-zeroed buffers.
  *   act : a[e] = SiLU(P[i_e] + Q[j_e] + r_e w_r + d0_e w_d)
