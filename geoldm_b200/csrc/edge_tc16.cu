@@ -95,7 +95,19 @@ struct Args {
   float norm_constant, coords_range;
   int attention, use_tanh;
   float rz_scale;           // 1 + RZ_BIAS_PER_MMA * (#MMAs accumulated per output)
+  // RAW mode, optional: bit pattern of max|A| over the whole operand (device scalar).  The producers multiply A by the
+  // power of two that puts that maximum in [2^13, 2^14) and the epilogue divides it out again (both exact): gradient
+  // operands, which are 1 / batch-size small, stay inside the normal fp16 range of the hi | lo split.
+  const unsigned* a_amax_bits;
 };
+
+// power-of-two exponent e with amax 2^e in [2^13, 2^14) (0 for amax == 0), from the fp32 bit pattern of amax
+__device__ __forceinline__ int amax_exponent(unsigned bits) {
+  const float amax = __uint_as_float(bits);
+  int e = 0;
+  if (amax > 0.f) { int ex; frexpf(amax, &ex); e = 14 - ex; }
+  return max(-100, min(100, e));
+}
 
 template <int H, int MODE>
 struct Smem {
@@ -365,6 +377,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
     const int chunk = pt & 7;
     const int rg = pt >> 3;
     uint32_t it = 0, pit = 0;
+    float a_mul = 1.0f;
+    if (MODE == MODE_RAW && a.a_amax_bits) a_mul = ldexpf(1.0f, amax_exponent(__ldg(a.a_amax_bits)));
     TC_PROF(long long tp_wait = 0; long long tp_comp = 0; long long tp_fence = 0; long long tp_meta = 0;)
     for (int iter = 0; iter < n_iter; ++iter) {
       TC_PROF(const long long tm0 = clock64();)
@@ -391,7 +405,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
           pP[p] = a.a1 + (size_t)grow * a.k1 + 4 * chunk;
           pQ[p] = a.a2 ? a.a2 + (size_t)grow * a.k2 + 4 * chunk : nullptr;
         } else {
-          const int i = a.edge_i[grow];
+          const int i = (MODE == MODE_RAW && a.edge_i == nullptr) ? grow : a.edge_i[grow];   // RAW without a row table: A row = tile row
           pP[p] = a.pq + (size_t)i * a.pq_ld + 4 * chunk;
           oP[p] = (uint32_t)(i - meta.x) * 256u + 16u * chunk;
           if (i != prev_i) lmask |= 1u << p;
@@ -549,7 +563,7 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
                 }
               } else {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) e[c] = vv[c];
+                for (int c = 0; c < 8; ++c) e[c] = vv[c] * a_mul;
               }
               uint4 hi, lo;
               split_f16x8(e, hi, lo);
@@ -596,7 +610,8 @@ __global__ void __launch_bounds__(Roles<MODE>::NTHREADS, 1) tc16_kernel(const Ar
     const uint32_t s_wo = s_b2 + H * 4;
     const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + hf * HC;
     // 2^-e of the weight images times the round-toward-zero compensation
-    const float scale = __ldg(reinterpret_cast<const float*>(a.w_pack)) * a.rz_scale;
+    float scale = __ldg(reinterpret_cast<const float*>(a.w_pack)) * a.rz_scale;
+    if (MODE == MODE_RAW && a.a_amax_bits) scale *= ldexpf(1.0f, -amax_exponent(__ldg(a.a_amax_bits)));
     auto release_acc = [&](int region) {
       __syncwarp();
       if (lane == 0) { if (crank != 0) mbar_arrive_remote(&acc_empty[region], 0); else mbar_arrive(&acc_empty[region]); }
@@ -1051,7 +1066,7 @@ __global__ void pack16_amax_kernel(const float* __restrict__ w, size_t n, unsign
   if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like uints
 }
 
-__global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int k, uint8_t* __restrict__ pack) {
+__global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int k, uint8_t* __restrict__ pack, int transposed) {
   // scale 2^e with max|w| 2^e in [2^13, 2^14)  (zero matrix: e = 0)
   const float amax = __uint_as_float(*reinterpret_cast<const unsigned*>(pack + 4));
   int e = 0;
@@ -1065,7 +1080,8 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
   const int nb = n / H, nl = n % H, slab = kk / 64, ko = kk % 64;
   const int kl = 8 * ((ko & 31) >> 2) + (ko & 3) + 4 * (ko >> 5);   // position inside the slab after the K permutation
   const int n_slabs = k / 64;
-  const float v = w[idx] * scale;                                   // exact (power of two)
+  // transposed: the source is [k][n_out] row-major (a Linear weight read as the operand of its input-gradient GEMM)
+  const float v = (transposed ? w[(size_t)kk * n_out + n] : w[idx]) * scale;   // exact (power of two)
   const __half hi = __float2half_rn(v);
   const __half lo = __float2half_rn(v - __half2float(hi));
   const int NH = H / 2, half = nl / NH, rl = nl % NH;
@@ -1620,6 +1636,27 @@ int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, 
   return launch_h<MODE_DENSE>(H, a, st);
 }
 
+// out[m][H] = a[m][H] (row stride ld) * W^T with a power-of-two pre-scaling of A taken from its own maximum: the
+// input-gradient GEMM dX = dY W of a square Linear layer (dY is 1 / batch-size small: unscaled it leaves the normal fp16
+// range and the hi | lo split loses its low half).  amax_scratch: 4 bytes of device memory.
+int launch_linear_tc16_grad(int H, const float* a_rows, int ld, const void* w_pack, float* out, int m, unsigned* amax_scratch,
+                            cudaStream_t st) {
+  GEOLDM_REQUIRE(w_pack != nullptr && amax_scratch != nullptr, "linear_tc16_grad: w_pack / amax_scratch missing%s", "");
+  GEOLDM_REQUIRE(ld % 4 == 0 && ld >= H && (reinterpret_cast<uintptr_t>(a_rows) & 15) == 0, "linear_tc16_grad: ld=%d", ld);
+  if (m == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned), st);
+  GEOLDM_REQUIRE(e == cudaSuccess, "linear_tc16_grad: memset: %s", cudaGetErrorString(e));
+  GEOLDM_REQUIRE(ld == H, "linear_tc16_grad: the operand must be dense (ld=%d, H=%d)", ld, H);
+  const size_t tot = (size_t)m * H;
+  pack16_amax_kernel<<<(unsigned)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184), 256, 0, st>>>(a_rows, tot, amax_scratch);
+  GEOLDM_CHECK_LAUNCH("pack16_amax_kernel(grad)");
+  Args a{};
+  a.n_tile = (m + TM - 1) / TM; a.n_rows = m; a.tile_row = nullptr; a.n_blocks = 1; a.n_slabs = H / BK;
+  a.pq = a_rows; a.pq_ld = ld; a.edge_i = nullptr; a.w_pack = reinterpret_cast<const uint8_t*>(w_pack); a.out = out; a.ldo = H;
+  a.a_amax_bits = amax_scratch;
+  return launch_h<MODE_RAW>(H, a, st);
+}
+
 int launch_node_chain16(int H, const float* h, const float* agg, float agg_div, const void* pack1, const float* b1,
                         const void* pack2, const float* b2, const void* pack3, const float* b3, int n_pb, float* h_out,
                         float* pq_out, float* zero_buf, int m, cudaStream_t st) {
@@ -1674,7 +1711,18 @@ size_t geoldm_tc_pack16_bytes(int H, int n_out, int k) {
   return geoldm::PACK_HDR + (size_t)n_out * k * 2 * sizeof(__half);
 }
 
+static int tc_pack16_impl(int H, const float* w, int n_out, int k, void* pack, void* stream, int transposed);
 int geoldm_tc_pack16(int H, const float* w, int n_out, int k, void* pack, void* stream) {
+  return tc_pack16_impl(H, w, n_out, k, pack, stream, 0);
+}
+int geoldm_tc_pack16_t(int H, const float* w_kn, int n_out, int k, void* pack, void* stream) {
+  return tc_pack16_impl(H, w_kn, n_out, k, pack, stream, 1);
+}
+int geoldm_linear_tc_grad(int H, const float* dy, int ld, const void* w_pack, float* out, int m, void* amax_scratch,
+                          void* stream) {
+  return geoldm::launch_linear_tc16_grad(H, dy, ld, w_pack, out, m, reinterpret_cast<unsigned*>(amax_scratch), (cudaStream_t)stream);
+}
+static int tc_pack16_impl(int H, const float* w, int n_out, int k, void* pack, void* stream, int transposed) {
   GEOLDM_REQUIRE(H % 64 == 0 && H <= 256 && n_out % H == 0 && k % 64 == 0, "tc_pack16: H=%d n_out=%d k=%d", H, n_out, k);
   const size_t tot = (size_t)n_out * k;
   if (tot == 0) return 0;
@@ -1684,7 +1732,7 @@ int geoldm_tc_pack16(int H, const float* w, int n_out, int k, void* pack, void* 
   unsigned* amax = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(pack) + 4);
   geoldm::pack16_amax_kernel<<<(unsigned)((tot + 255) / 256 < 1024 ? (tot + 255) / 256 : 1024), 256, 0, st>>>(w, tot, amax);
   GEOLDM_CHECK_LAUNCH("pack16_amax_kernel");
-  geoldm::pack16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(H, w, n_out, k, reinterpret_cast<uint8_t*>(pack));
+  geoldm::pack16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(H, w, n_out, k, reinterpret_cast<uint8_t*>(pack), transposed);
   GEOLDM_CHECK_LAUNCH("pack16_kernel");
   return 0;
 }

@@ -35,11 +35,11 @@ __global__ void __launch_bounds__(NT, 2) linear_kernel(const LinArgs a) {
   const int wk = t >> 4, wc4 = (t & 15) * 4;
   const bool wvalid = col0 + wc4 < a.n;
 
-  float acc[8][4];
+  // accumulators as packed fp32 pairs along the output columns (fma.rn.f32x2: two IEEE FMAs per issue slot; the plain
+  // three-register FFMA issues every second cycle per scheduler on sm_100), same products and summation order
+  f32x2 acc2[8][2];
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int r = 0; r < 8; ++r) acc2[r][0] = acc2[r][1] = pk2(0.f, 0.f);
 
   float4 pf0, pf1;
   auto a_load = [&](int s) {
@@ -84,15 +84,20 @@ __global__ void __launch_bounds__(NT, 2) linear_kernel(const LinArgs a) {
       float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + rg * 4]);
       float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][cg * 4]);
       float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float bv[4] = {b.x, b.y, b.z, b.w};
+      const f32x2 b01 = pk2(b.x, b.y), b23 = pk2(b.z, b.w);
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+      for (int r = 0; r < 8; ++r) {
+        const f32x2 aa = pk2(av[r], av[r]);
+        acc2[r][0] = fma2(aa, b01, acc2[r][0]);
+        acc2[r][1] = fma2(aa, b23, acc2[r][1]);
+      }
     }
     if (s + 1 < NS) a_store(buf ^ 1);
   }
 
+  float acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { upk2(acc2[r][0], acc[r][0], acc[r][1]); upk2(acc2[r][1], acc[r][2], acc[r][3]); }
   const int col = col0 + cg * 4;
   if (col < a.n) {
     float4 bias = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -114,72 +119,77 @@ __global__ void __launch_bounds__(NT, 2) linear_kernel(const LinArgs a) {
 
 // Same contraction for node-level row counts (a few thousand rows): 32 x 64 tiles, 128 threads, 4 x 4 outputs per thread.
 // At m = 1158 (64 QM9 molecules) the 128 x 64 tiles above are 30 CTAs on 148 SMs, each walking the whole K loop: 18 us per
-// launch, 144 launches per training step; four times as many, four times shorter CTAs bring that to the launch-latency floor.
-constexpr int SBM = 32, SNT = 128, SAST = SBM + 4;
+// launch, 144 launches per training step; four times as many, four times shorter CTAs bring that to the latency of the K
+// loop itself.  That loop is a chain of (L2 load -> shared memory -> barrier) per 16-wide slab with next to no arithmetic to
+// hide it behind, so both operands arrive through a 4-stage cp.async ring: three slabs are in flight while one is consumed
+// (A in its global row-major form: a thread reads four k values of a row as one 16-byte vector).
+constexpr int SBM = 32, SNT = 128, SST = 4, SAK = BK + 4;
 template <int EPI>
 __global__ void __launch_bounds__(SNT, 8) linear_small_kernel(const LinArgs a) {
-  __shared__ __align__(16) float As[2][BK][SAST];
-  __shared__ __align__(16) float Ws[2][BK][BN];
+  __shared__ __align__(16) float As[SST][SBM][SAK];
+  __shared__ __align__(16) float Ws[SST][BK][BN];
   const int t = threadIdx.x;
   const int rg = t >> 4, cg = t & 15;            // 8 x 16 thread grid, 4 x 4 outputs each
   const int row0 = blockIdx.y * SBM, col0 = blockIdx.x * BN;
   const int K = a.k1 + a.k2, NS = K / BK;
-  const int lrow = t >> 2, lk = (t & 3) * 4;     // activation loader: (row, 4 consecutive k)
-  const bool lvalid = row0 + lrow < a.m;
+  const int lrow = t >> 2, lk = (t & 3) * 4;     // activation loader: (row, 4 consecutive k) = one 16-byte copy per slab
+  const int grow = min(row0 + lrow, a.m - 1);    // rows past the end: a copy of the last row, computed and never stored
   const int wk = t >> 4, wc4 = (t & 15) * 4;     // weight loader: rows wk and wk + 8 of the slab, 4 consecutive columns
   const bool wvalid = col0 + wc4 < a.n;
-  float acc[4][4];
+  f32x2 acc2[4][2];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-  float4 pf;
-  auto a_load = [&](int s) {
-    pf = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lvalid) {
-      const int k0 = s * BK + lk;
-      const float* src = (k0 < a.k1) ? a.a1 + (size_t)(row0 + lrow) * a.k1 + k0
-                                     : a.a2 + (size_t)(row0 + lrow) * a.k2 + (k0 - a.k1);
-      pf = __ldg(reinterpret_cast<const float4*>(src));
-      if (k0 >= a.k1 && a.a2_div != 1.0f) {
-        const float d = a.a2_div;
-        pf.x = __fdiv_rn(pf.x, d); pf.y = __fdiv_rn(pf.y, d); pf.z = __fdiv_rn(pf.z, d); pf.w = __fdiv_rn(pf.w, d);
-      }
-    }
-  };
-  auto a_store = [&](int buf) {
-    As[buf][lk][lrow] = pf.x; As[buf][lk + 1][lrow] = pf.y; As[buf][lk + 2][lrow] = pf.z; As[buf][lk + 3][lrow] = pf.w;
-  };
-  auto w_load = [&](int s, int buf) {
+  for (int r = 0; r < 4; ++r) acc2[r][0] = acc2[r][1] = pk2(0.f, 0.f);
+  auto load = [&](int s, int st) {
+    const int k0 = s * BK + lk;
+    const float* src = (k0 < a.k1) ? a.a1 + (size_t)grow * a.k1 + k0 : a.a2 + (size_t)grow * a.k2 + (k0 - a.k1);
+    cp_async16(&As[st][lrow][lk], src);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int kk = wk + 8 * h;
-      if (wvalid) cp_async16(&Ws[buf][kk][wc4], a.wt + (size_t)(s * BK + kk) * a.n + col0 + wc4);
-      else *reinterpret_cast<float4*>(&Ws[buf][kk][wc4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (wvalid) cp_async16(&Ws[st][kk][wc4], a.wt + (size_t)(s * BK + kk) * a.n + col0 + wc4);
+      else *reinterpret_cast<float4*>(&Ws[st][kk][wc4]) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    cp_async_commit();
   };
-  w_load(0, 0);
-  a_load(0);
-  a_store(0);
-  for (int s = 0; s < NS; ++s) {
-    const int buf = s & 1;
-    cp_async_wait<0>();
-    __syncthreads();
-    if (s + 1 < NS) { w_load(s + 1, buf ^ 1); a_load(s + 1); }
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 av4 = *reinterpret_cast<const float4*>(&As[buf][k][rg * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][cg * 4]);
-      const float av[4] = {av4.x, av4.y, av4.z, av4.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
-    }
-    if (s + 1 < NS) a_store(buf ^ 1);
+  for (int s = 0; s < SST - 1; ++s) {            // one commit group per slab, empty groups past the end keep the count uniform
+    if (s < NS) load(s, s);
+    cp_async_commit();
   }
+  for (int s = 0; s < NS; ++s) {
+    cp_async_wait<SST - 2>();                    // slab s has landed (this thread's copies; the barrier covers the others)
+    __syncthreads();                             // ... and every thread is done with the stage refilled below (slab s - 1)
+    if (s + SST - 1 < NS) load(s + SST - 1, (s + SST - 1) % SST);
+    cp_async_commit();
+    const int st = s % SST;
+    const bool div = s * BK >= a.k1 && a.a2_div != 1.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      float av[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[st][rg * 4 + r][k4]);
+        av[r][0] = v.x; av[r][1] = v.y; av[r][2] = v.z; av[r][3] = v.w;
+        if (div) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) av[r][kk] = __fdiv_rn(av[r][kk], a.a2_div);
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 b = *reinterpret_cast<const float4*>(&Ws[st][k4 + kk][cg * 4]);
+        const f32x2 b01 = pk2(b.x, b.y), b23 = pk2(b.z, b.w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const f32x2 aa = pk2(av[r][kk], av[r][kk]);
+          acc2[r][0] = fma2(aa, b01, acc2[r][0]);
+          acc2[r][1] = fma2(aa, b23, acc2[r][1]);
+        }
+      }
+    }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { upk2(acc2[r][0], acc[r][0], acc[r][1]); upk2(acc2[r][1], acc[r][2], acc[r][3]); }
   const int col = col0 + cg * 4;
   if (col < a.n) {
     const float4 bias = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);

@@ -20,11 +20,11 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
   const int tr = t >> 4, tc = t & 15;            // 16 x 16 threads, 4 x 4 outputs each
   // loaders: thread -> (row = t / 16, 4 consecutive columns)
   const int lr = t >> 4, lc = (t & 15) * 4;
-  float acc[4][4];
+  // accumulators as packed fp32 pairs along the output columns: fma.rn.f32x2 performs two IEEE FMAs per issue slot (the
+  // plain three-register FFMA issues every second cycle per scheduler on sm_100), same products and summation order
+  f32x2 acc2[4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = pk2(0.f, 0.f);
 
   // global -> registers (issued before the FMAs of the current slab) -> shared (after them): the L2 latency of the next
   // 16-row slab is hidden behind 256 FMAs per thread instead of being exposed at every slab
@@ -61,23 +61,36 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
     for (int mm = 0; mm < TN_BM; ++mm) {
       const float4 av = *reinterpret_cast<const float4*>(&As[buf][mm][tr * 4]);
       const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][mm][tc * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const f32x2 b01 = pk2(bv.x, bv.y), b23 = pk2(bv.z, bv.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        const f32x2 aa = pk2(ar[i], ar[i]);
+        acc2[i][0] = fma2(aa, b01, acc2[i][0]);
+        acc2[i][1] = fma2(aa, b23, acc2[i][1]);
+      }
     }
     if (more) s_store(buf ^ 1);
     __syncthreads();
     buf ^= 1;
   }
+  const bool vec_out = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15u) == 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { upk2(acc2[i][0], acc[i][0], acc[i][1]); upk2(acc2[i][1], acc[i][2], acc[i][3]); }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int nn = n0 + tr * 4 + i;
     if (nn >= n) continue;
+    const int kk0 = k0 + tc * 4;
+    if (vec_out && kk0 + 3 < k) {     // one 16-byte vector reduction instead of four scalar ones (L2 reduction operations / 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + (size_t)nn * ldc + kk0), "f"(acc[i][0]),
+                   "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int kk = k0 + tc * 4 + j;
+      const int kk = kk0 + j;
       if (kk < k) atomicAdd(c + (size_t)nn * ldc + kk, acc[i][j]);
     }
   }
@@ -508,7 +521,7 @@ extern "C" int geoldm_gemm_tn_bias(const float* a, int lda, const float* b, int 
   GEOLDM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "gemm_tn: lda=%d ldb=%d must be multiples of 4", lda, ldb);
   if (m == 0 || n == 0 || k == 0) return 0;
   const int tiles = ((n + TN_BN - 1) / TN_BN) * ((k + TN_BK - 1) / TN_BK);
-  int splits = (4 * 148 + tiles - 1) / tiles;                  // aim at ~4 CTAs per SM
+  int splits = (3 * 148) / tiles;                              // one resident wave: 3 CTAs of 66 registers x 256 threads per SM
   const int max_splits = (m + 4 * TN_BM - 1) / (4 * TN_BM);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

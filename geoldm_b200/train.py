@@ -28,9 +28,10 @@ def _stream(t):
 
 
 # Edge-level GEMMs (M = number of edges) of the autograd path run on the tcgen05 fp16-split kernel (fp32-equivalent
-# products, csrc/edge_tc16.cu DENSE mode) in the FORWARD direction, where the A operand is an O(1) activation; input and
-# weight gradients stay on the fp32 FFMA kernels (gradient operands underflow fp16, see _LinearFn.backward), as do the
-# node-level GEMMs (a few tiles: the launch is cheaper than packing a weight image).  GEOLDM_TRAIN_TC=0 disables it.
+# products, csrc/edge_tc16.cu DENSE mode) in the FORWARD direction, where the A operand is an O(1) activation, and in the
+# input-gradient direction with the gradient operand pre-scaled by a power of two (see _LinearFn.backward); weight
+# gradients stay on the fp32 FFMA kernel, as do the node-level GEMMs (a few tiles: the launch is cheaper than packing a
+# weight image).  GEOLDM_TRAIN_TC=0 disables it.
 _TC_MIN_ROWS = 4096
 
 
@@ -63,7 +64,7 @@ def _tc_linear(x, w_nk, bias, M, K, N):
 
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b on the geoldm_b200 GEMM kernels, x [M,K], W [N,K] (PyTorch layout): fp16-split tcgen05 for the forward
-    at edge-level row counts, fp32 FFMA otherwise and for dX / dW."""
+    and (square layers) the input gradient at edge-level row counts, fp32 FFMA otherwise and for dW."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -91,14 +92,23 @@ class _LinearFn(torch.autograd.Function):
         N = weight.shape[0]
         L = _lib.lib()
         dx = dw = db = None
-        # dX stays on the fp32 FFMA kernel: its A operand is a GRADIENT, whose magnitude scales with 1 / batch size and
-        # falls below the normal fp16 range (6e-5) - the fp16-split products then lose their low halves.  Measured: fine
-        # at 64 molecules, 4.7 relative error on a bias gradient at 256 molecules per GPU (scripts/train_check.py).
+        # dX = dY W.  Edge-level square layers: fp16-split tensor-core kernel with dY pre-scaled by a power of two taken
+        # from its own maximum (geoldm_linear_tc_grad) - dY is a GRADIENT, 1 / batch-size small, and leaves the normal fp16
+        # range unscaled (measured before the scaling existed: fine at 64 molecules, 4.7 relative error on a bias gradient
+        # at 256 molecules per GPU, scripts/train_check.py).  Everything else: fp32 FFMA kernel.
         if ctx.needs_input_grad[0]:
             w = weight.contiguous()                       # [N][K] is already k-major for dX = dY W
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
-            _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
-                                       _stream(x)), "geoldm_linear(dX)")
+            if N == K and K in (64, 128, 192, 256) and _tc_ok(M, N, K):
+                st = _stream(x)
+                pack = torch.empty(L.geoldm_tc_pack16_bytes(K, K, N), dtype=torch.uint8, device=x.device)
+                _lib.check(L.geoldm_tc_pack16_t(K, _lib.ptr(w), K, N, _lib.ptr(pack), st), "geoldm_tc_pack16_t(dX)")
+                amax = torch.empty(1, dtype=torch.int32, device=x.device)
+                _lib.check(L.geoldm_linear_tc_grad(K, _lib.ptr(dy), N, _lib.ptr(pack), _lib.ptr(dx), M, _lib.ptr(amax), st),
+                           "geoldm_linear_tc_grad(dX)")
+            else:
+                _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
+                                           _stream(x)), "geoldm_linear(dX)")
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             # dW and the bias gradient from ONE pass over dY (geoldm_gemm_tn_bias: the k0 == 0 blocks also add up the dY

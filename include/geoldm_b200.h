@@ -216,6 +216,14 @@ int geoldm_node_chain(int H, const float* h, const float* agg, float agg_div, co
 int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2, int k2, float a2_div,
                      const void* w_pack, int n_blocks, const float* bias, const float* res, int epi, float* out,
                      int m, void* stream);
+/* input-gradient GEMM of a square Linear layer on the fp16-split tensor-core kernel:  out[m][H] = dy[m][H] * W  with W
+ * [H out-features][H in-features] packed by geoldm_tc_pack16_t (the transposed operand).  dy is a GRADIENT (1 / batch-size
+ * small): the kernel scales it by the power of two that puts max|dy| in [2^13, 2^14) before the fp16 hi | lo split and
+ * divides it out in the epilogue (both exact), so the result is as accurate as the forward GEMM regardless of the
+ * magnitude of dy.  ld == H; amax_scratch: 4 bytes of device memory (overwritten). */
+int geoldm_tc_pack16_t(int H, const float* w_kn, int n_out, int k, void* pack, void* stream);
+int geoldm_linear_tc_grad(int H, const float* dy, int ld, const void* w_pack, float* out, int m, void* amax_scratch,
+                          void* stream);
 /* descriptor / swizzle / pipeline self-test: out[row][0:H] = sum_k a[src_row[row]][k] * W[:, k] with a row stride
  * of 2H floats (the P|Q layout), rows split into tiles by tile_row like the edge kernels */
 int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, const int* tile_row, int n_tile,
