@@ -88,6 +88,10 @@ _SIGS = {
     "geoldm_train_edge_tail_fwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp]),
     "geoldm_train_edge_tail_bwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp,
                                              fp, fp, fp, fp, fp]),
+    "geoldm_train_coord2diff_fwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_float, fp, fp, fp]),
+    "geoldm_train_coord2diff_bwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_float, fp, fp, fp, fp]),
+    "geoldm_train_coord_step_fwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_int, C.c_float, C.c_float, fp, fp]),
+    "geoldm_train_coord_step_bwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_int, C.c_float, C.c_float, fp, fp, fp, fp]),
     "geoldm_train_bwd_blocks": (C.c_int, [C.c_int]),
     "geoldm_stability": (C.c_int, [C.c_int, fp, fp, fp, C.c_int, fp, fp, C.c_int, fp, fp, fp]),
     "geoldm_tc_read_stats": (C.c_int, [C.POINTER(C.c_ulonglong)]),

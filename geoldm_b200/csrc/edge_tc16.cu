@@ -1059,11 +1059,27 @@ int launch_h(int H, const Args& a, cudaStream_t st, const StageMaps* sm = nullpt
 // fp16 split of the scaled weights, one thread per element: W[n][k] -> block n/H, slab k/64, N-half, hi|lo images
 __global__ void pack16_amax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ amax_bits) {
   float m = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(w[i]));
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(w) & 15u) == 0) {             // 16-byte loads over the aligned bulk, scalars for the tail
+    const size_t n4 = n / 4;
+    for (size_t i = tid; i < n4; i += nthr) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (size_t i = 4 * n4 + tid; i < n; i += nthr) m = fmaxf(m, fabsf(w[i]));
+  } else {
+    for (size_t i = tid; i < n; i += nthr) m = fmaxf(m, fabsf(w[i]));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like uints
+  // one atomic per block (every warp on the same word serialises in L2: ~10 k atomics for an [E, H] operand before)
+  __shared__ float wmax[32];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (unsigned k = 1; k < (blockDim.x + 31) / 32; ++k) m = fmaxf(m, wmax[k]);
+    atomicMax(amax_bits, __float_as_uint(m));                    // non-negative floats order like uints
+  }
 }
 
 __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int k, uint8_t* __restrict__ pack, int transposed) {
@@ -1648,7 +1664,7 @@ int launch_linear_tc16_grad(int H, const float* a_rows, int ld, const void* w_pa
   GEOLDM_REQUIRE(e == cudaSuccess, "linear_tc16_grad: memset: %s", cudaGetErrorString(e));
   GEOLDM_REQUIRE(ld == H, "linear_tc16_grad: the operand must be dense (ld=%d, H=%d)", ld, H);
   const size_t tot = (size_t)m * H;
-  pack16_amax_kernel<<<(unsigned)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184), 256, 0, st>>>(a_rows, tot, amax_scratch);
+  pack16_amax_kernel<<<(unsigned)((tot + 1023) / 1024 < 592 ? (tot + 1023) / 1024 : 592), 256, 0, st>>>(a_rows, tot, amax_scratch);
   GEOLDM_CHECK_LAUNCH("pack16_amax_kernel(grad)");
   Args a{};
   a.n_tile = (m + TM - 1) / TM; a.n_rows = m; a.tile_row = nullptr; a.n_blocks = 1; a.n_slabs = H / BK;
@@ -1730,7 +1746,7 @@ static int tc_pack16_impl(int H, const float* w, int n_out, int k, void* pack, v
   cudaError_t e = cudaMemsetAsync(pack, 0, geoldm::PACK_HDR, st);
   if (e != cudaSuccess) { geoldm::set_error("tc_pack16: memset: %s", cudaGetErrorString(e)); return -2; }
   unsigned* amax = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(pack) + 4);
-  geoldm::pack16_amax_kernel<<<(unsigned)((tot + 255) / 256 < 1024 ? (tot + 255) / 256 : 1024), 256, 0, st>>>(w, tot, amax);
+  geoldm::pack16_amax_kernel<<<(unsigned)((tot + 1023) / 1024 < 592 ? (tot + 1023) / 1024 : 592), 256, 0, st>>>(w, tot, amax);
   GEOLDM_CHECK_LAUNCH("pack16_amax_kernel");
   geoldm::pack16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(H, w, n_out, k, reinterpret_cast<uint8_t*>(pack), transposed);
   GEOLDM_CHECK_LAUNCH("pack16_kernel");

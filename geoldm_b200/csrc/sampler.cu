@@ -91,16 +91,26 @@ __global__ void embed_kernel(int n_node, int H, int F, const float* __restrict__
   h[idx] = acc + b[f];
 }
 
-// out[N][Fo] = h[N][H] * W^T + b, W [Fo][H]; one warp per node
+// out[N][Fo] = h[N][H] * W^T + b, W [Fo][H]; one warp per (node, chunk of OUTPROJ_FC outputs), the node's row kept in
+// registers across the outputs.  (The VAE encoder's EGNN has Fo = hidden_nf outputs: one warp walking all of them in turn
+// took 0.25 ms per launch at 1158 nodes.)
+constexpr int OUTPROJ_FC = 16;
 __global__ void outproj_kernel(int n_node, int H, int Fo, const float* __restrict__ h, const float* __restrict__ w,
                                const float* __restrict__ b, float* __restrict__ out) {
   const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (node >= n_node) return;
   const float* hr = h + (size_t)node * H;
-  for (int f = 0; f < Fo; ++f) {
+  float hv[8];                                   // the first 256 columns
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hv[j] = (lane + 32 * j < H) ? hr[lane + 32 * j] : 0.f;
+  const int f0 = blockIdx.y * OUTPROJ_FC, f1 = min(Fo, f0 + OUTPROJ_FC);
+  for (int f = f0; f < f1; ++f) {
     float acc = 0.f;
-    for (int k = lane; k < H; k += 32) acc = fmaf(hr[k], w[(size_t)f * H + k], acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (lane + 32 * j < H) acc = fmaf(hv[j], w[(size_t)f * H + lane + 32 * j], acc);
+    for (int k = lane + 256; k < H; k += 32) acc = fmaf(hr[k], w[(size_t)f * H + k], acc);   // H > 256: rest of the row from memory
     acc = warp_sum(acc);
     if (lane == 0) out[(size_t)node * Fo + f] = acc + b[f];
   }
@@ -380,7 +390,7 @@ int launch_embed(int n_node, int H, int F, const float* h_in, const float* w, co
 int launch_outproj(int n_node, int H, int Fo, const float* h, const float* w, const float* b, float* out,
                    cudaStream_t st) {
   if (n_node == 0) return 0;
-  outproj_kernel<<<(n_node * 32 + 127) / 128, 128, 0, st>>>(n_node, H, Fo, h, w, b, out);
+  outproj_kernel<<<dim3((n_node * 32 + 127) / 128, (Fo + OUTPROJ_FC - 1) / OUTPROJ_FC), 128, 0, st>>>(n_node, H, Fo, h, w, b, out);
   GEOLDM_CHECK_LAUNCH("outproj_kernel");
   return 0;
 }

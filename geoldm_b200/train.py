@@ -269,6 +269,61 @@ class _SplitFirstFn(torch.autograd.Function):
         return torch.cat(parts, dim=1), (None if dbpq is None else dbpq[:H])
 
 
+class _Coord2DiffFn(torch.autograd.Function):
+    """coord2diff (egnn_new.py:249-255) as one launch forward and one backward: x [N, 3] -> r [E, 1] = |x_i - x_j|^2 and
+    (want_u) u [E, 3] = (x_i - x_j) / (sqrt(r + 1e-8) + norm_constant)."""
+
+    @staticmethod
+    def forward(ctx, x, ei32, ej32, norm_constant, want_u):
+        xc = x.contiguous()
+        E = ei32.numel()
+        r = torch.empty(E, 1, device=x.device, dtype=torch.float32)
+        u = torch.empty(E, 3, device=x.device, dtype=torch.float32) if want_u else None
+        _lib.check(_lib.lib().geoldm_train_coord2diff_fwd(E, _lib.ptr(xc), _lib.ptr(ei32), _lib.ptr(ej32),
+                                                          float(norm_constant), _lib.ptr(r), _lib.ptr(u), _stream(x)),
+                   "train_coord2diff_fwd")
+        ctx.save_for_backward(xc, ei32, ej32)
+        ctx.c = float(norm_constant)
+        ctx.set_materialize_grads(False)
+        return r, u
+
+    @staticmethod
+    def backward(ctx, gr, gu):
+        xc, ei32, ej32 = ctx.saved_tensors
+        gx = torch.zeros_like(xc)
+        gr = None if gr is None else gr.contiguous()
+        gu = None if gu is None else gu.contiguous()
+        _lib.check(_lib.lib().geoldm_train_coord2diff_bwd(ei32.numel(), _lib.ptr(xc), _lib.ptr(ei32), _lib.ptr(ej32), ctx.c,
+                                                          _lib.ptr(gr), _lib.ptr(gu), _lib.ptr(gx), _stream(xc)),
+                   "train_coord2diff_bwd")
+        return gx, None, None, None, None
+
+
+class _CoordStepFn(torch.autograd.Function):
+    """Coordinate update of EquivariantUpdate (egnn_new.py:91-99): step [N, 3] = segment sum over receivers of
+    u * (tanh(sc) * coords_range | sc) / normalization_factor, one launch forward and one backward."""
+
+    @staticmethod
+    def forward(ctx, u, sc, ei32, n_node, use_tanh, coords_range, div):
+        u, sc = u.contiguous(), sc.contiguous()
+        step = torch.zeros(n_node, 3, device=u.device, dtype=torch.float32)
+        ctx.cfg = (int(bool(use_tanh)), float(coords_range), float(div))
+        _lib.check(_lib.lib().geoldm_train_coord_step_fwd(ei32.numel(), _lib.ptr(u), _lib.ptr(sc), _lib.ptr(ei32), *ctx.cfg,
+                                                          _lib.ptr(step), _stream(u)), "train_coord_step_fwd")
+        ctx.save_for_backward(u, sc, ei32)
+        return step
+
+    @staticmethod
+    def backward(ctx, gstep):
+        u, sc, ei32 = ctx.saved_tensors
+        gstep = gstep.contiguous()
+        gu, gsc = torch.empty_like(u), torch.empty_like(sc)
+        _lib.check(_lib.lib().geoldm_train_coord_step_bwd(ei32.numel(), _lib.ptr(u), _lib.ptr(sc), _lib.ptr(ei32), *ctx.cfg,
+                                                          _lib.ptr(gstep), _lib.ptr(gu), _lib.ptr(gsc), _stream(u)),
+                   "train_coord_step_bwd")
+        return gu, gsc, None, None, None, None, None
+
+
 def _fused_ok(h, H):
     return h.is_cuda and h.dtype == torch.float32 and H <= 256 and H % 16 == 0
 
@@ -302,13 +357,19 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
         div = float(batch.n_max)
     else:
         div = float(egnn.normalization_factor)
-    fused = _fused_ok(h, H)
-    d0, _ = _coord2diff(x, ei, ej, 1.0)
+    fused = _fused_ok(h, H) and x.is_cuda and x.dtype == torch.float32
+    if fused:
+        d0, _ = _Coord2DiffFn.apply(x, e32[0], e32[1], 1.0, False)
+    else:
+        d0, _ = _coord2diff(x, ei, ej, 1.0)
     x0, dx = x, None        # the accumulated displacement is carried next to x: the dynamics' velocity x_final - x is
     h = F.linear(h, egnn.embedding.weight, egnn.embedding.bias)   # then exact instead of a cancelling difference
     for b in range(egnn.n_layers):
         blk = getattr(egnn, f"e_block_{b}")
-        r, u = _coord2diff(x, ei, ej, float(egnn.norm_constant))
+        if fused:
+            r, u = _Coord2DiffFn.apply(x, e32[0], e32[1], float(egnn.norm_constant), True)
+        else:
+            r, u = _coord2diff(x, ei, ej, float(egnn.norm_constant))
         for s in range(egnn.inv_sublayers):
             g = getattr(blk, f"gcl_{s}")
             a1 = _edge_pre(h, g.edge_mlp[0], ei, ej, r, d0, H, e32)
@@ -332,8 +393,11 @@ def egnn_forward_train(egnn, h, x, batch: RaggedBatch):
         else:
             m2 = F.silu(linear(a2, q.coord_mlp[2].weight, q.coord_mlp[2].bias))
             sc = F.linear(m2, q.coord_mlp[4].weight)
-        trans = u * torch.tanh(sc) * egnn.coords_range if egnn.tanh else u * sc
-        step = torch.zeros(N, 3, device=x.device, dtype=x.dtype).index_add_(0, ei, trans) / div
+        if fused:
+            step = _CoordStepFn.apply(u, sc, e32[0], N, bool(egnn.tanh), float(egnn.coords_range), div)
+        else:
+            trans = u * torch.tanh(sc) * egnn.coords_range if egnn.tanh else u * sc
+            step = torch.zeros(N, 3, device=x.device, dtype=x.dtype).index_add_(0, ei, trans) / div
         dx = step if dx is None else dx + step
         x = x0 + dx
     h = F.linear(h, egnn.embedding_out.weight, egnn.embedding_out.bias)

@@ -257,6 +257,20 @@ int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float
                                double* dbw_scratch, /* [geoldm_train_bwd_blocks(n_edge) + 1] doubles, ZEROED once (the kernel leaves it zeroed), or
                                                      * NULL: dbw is accumulated with float atomics in arrival order (not reproducible) */
                                void* stream);
+/* coord2diff and the coordinate update of EquivariantUpdate for the autograd path, forward and backward (one thread per
+ * edge; egnn_new.py:249-255, 91-99):
+ *   r[e] = |x_i - x_j|^2, u[e][3] = (x_i - x_j) / (sqrt(r + 1e-8) + norm_constant)   (u may be NULL: r only)
+ *   bwd: gx [N][3] (caller-zeroed) += the gradient through r (gr [E], or NULL) and u (gu [E][3], or NULL)
+ *   step[i_e][3] (caller-zeroed) += u[e] * (use_tanh ? tanh(sc[e]) * coords_range : sc[e]) / div
+ *   bwd: gu [E][3], gsc [E] from gstep [N][3] */
+int geoldm_train_coord2diff_fwd(int n_edge, const float* x, const int* edge_i, const int* edge_j, float norm_constant,
+                                float* r, float* u, void* stream);
+int geoldm_train_coord2diff_bwd(int n_edge, const float* x, const int* edge_i, const int* edge_j, float norm_constant,
+                                const float* gr, const float* gu, float* gx, void* stream);
+int geoldm_train_coord_step_fwd(int n_edge, const float* u, const float* sc, const int* edge_i, int use_tanh,
+                                float coords_range, float div, float* step, void* stream);
+int geoldm_train_coord_step_bwd(int n_edge, const float* u, const float* sc, const int* edge_i, int use_tanh,
+                                float coords_range, float div, const float* gstep, float* gu, float* gsc, void* stream);
 /* number of thread blocks the backward edge kernels launch for n_edge edges (sizes dbw_scratch) */
 int geoldm_train_bwd_blocks(int n_edge);
 /* ---- evaluation side: bond-order stability of a ragged batch of molecules.
