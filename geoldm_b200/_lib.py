@@ -77,6 +77,7 @@ _SIGS = {
     "geoldm_tc_pack16_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "geoldm_tc_pack16": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
     "geoldm_tc_pack16_t": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
+    "geoldm_tc_pack16_pair": (C.c_int, [C.c_int, fp, fp, fp, fp]),
     "geoldm_linear_tc_grad": (C.c_int, [C.c_int, fp, C.c_int, fp, fp, C.c_int, fp, fp]),
     "geoldm_linear_tc": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, C.c_int,
                                    fp, C.c_int, fp]),

@@ -1082,22 +1082,11 @@ __global__ void pack16_amax_kernel(const float* __restrict__ w, size_t n, unsign
   }
 }
 
-__global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int k, uint8_t* __restrict__ pack, int transposed) {
-  // scale 2^e with max|w| 2^e in [2^13, 2^14)  (zero matrix: e = 0)
-  const float amax = __uint_as_float(*reinterpret_cast<const unsigned*>(pack + 4));
-  int e = 0;
-  if (amax > 0.f) { int ex; frexpf(amax, &ex); e = 14 - ex; }       // amax = f * 2^ex, f in [0.5, 1)
-  e = max(-100, min(100, e));
-  const float scale = ldexpf(1.0f, e);
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) *reinterpret_cast<float*>(pack) = ldexpf(1.0f, -e);
-  if (idx >= (size_t)n_out * k) return;
-  const int n = (int)(idx / k), kk = (int)(idx % k);
+// one element (output row n, input column kk) of W, already scaled, into the hi | lo images of a pack
+__device__ __forceinline__ void pack16_store(int H, int k, int n, int kk, float v, uint8_t* __restrict__ pack) {
   const int nb = n / H, nl = n % H, slab = kk / 64, ko = kk % 64;
   const int kl = 8 * ((ko & 31) >> 2) + (ko & 3) + 4 * (ko >> 5);   // position inside the slab after the K permutation
   const int n_slabs = k / 64;
-  // transposed: the source is [k][n_out] row-major (a Linear weight read as the operand of its input-gradient GEMM)
-  const float v = (transposed ? w[(size_t)kk * n_out + n] : w[idx]) * scale;   // exact (power of two)
   const __half hi = __float2half_rn(v);
   const __half lo = __float2half_rn(v - __half2float(hi));
   const int NH = H / 2, half = nl / NH, rl = nl % NH;
@@ -1106,6 +1095,65 @@ __global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int
   uint8_t* img = pack + PACK_HDR + (size_t)((nb * n_slabs + slab) * 2 + half) * 2 * (size_t)NH * 128;
   *reinterpret_cast<__half*>(img + off) = hi;
   *reinterpret_cast<__half*>(img + (size_t)NH * 128 + off) = lo;
+}
+// scale exponent e with max|w| 2^e in [2^13, 2^14)  (zero matrix: e = 0)
+__device__ __forceinline__ int pack16_exponent(float amax) {
+  int e = 0;
+  if (amax > 0.f) { int ex; frexpf(amax, &ex); e = 14 - ex; }       // amax = f * 2^ex, f in [0.5, 1)
+  return max(-100, min(100, e));
+}
+__global__ void pack16_kernel(int H, const float* __restrict__ w, int n_out, int k, uint8_t* __restrict__ pack, int transposed) {
+  const int e = pack16_exponent(__uint_as_float(*reinterpret_cast<const unsigned*>(pack + 4)));
+  const float scale = ldexpf(1.0f, e);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *reinterpret_cast<float*>(pack) = ldexpf(1.0f, -e);
+  if (idx >= (size_t)n_out * k) return;
+  const int n = (int)(idx / k), kk = (int)(idx % k);
+  // transposed: the source is [k][n_out] row-major (a Linear weight read as the operand of its input-gradient GEMM)
+  const float v = (transposed ? w[(size_t)kk * n_out + n] : w[idx]) * scale;   // exact (power of two)
+  pack16_store(H, k, n, kk, v, pack);
+}
+// Small square weights (training: they change every optimiser step and are packed once per step and direction): ONE
+// launch finds max|w| (every block on its own: the matrix is 64-256 KB of L2-resident data), writes the headers and its
+// share of both images - the forward operand (rows = output features) and the operand of the input-gradient GEMM (rows =
+// input features) - instead of memset + amax + pack launches per image.  (The image stores are scattered 2-byte writes: a
+// single block needs 100 us for them, 36 blocks 20 us; hence one element per thread, like pack16_kernel.)
+constexpr int PAIR_THREADS = 256;
+__global__ void __launch_bounds__(PAIR_THREADS) pack16_pair_kernel(int H, const float* __restrict__ w, uint8_t* __restrict__ pack_fwd,
+                                                                   uint8_t* __restrict__ pack_t) {
+  __shared__ float wmax[32];
+  __shared__ float s_amax;
+  const int tot = H * H;                          // a multiple of 4096
+  float m = 0.f;
+  if ((reinterpret_cast<uintptr_t>(w) & 15u) == 0) {
+    for (int i = threadIdx.x; i < tot / 4; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (unsigned q = 1; q < (blockDim.x + 31) / 32; ++q) m = fmaxf(m, wmax[q]);
+    s_amax = m;
+  }
+  __syncthreads();
+  const int e = pack16_exponent(s_amax);
+  const float scale = ldexpf(1.0f, e);
+  if (blockIdx.x == 0 && threadIdx.x < 2) {
+    uint8_t* p = threadIdx.x == 0 ? pack_fwd : pack_t;
+    if (p) { *reinterpret_cast<float*>(p) = ldexpf(1.0f, -e); *reinterpret_cast<unsigned*>(p + 4) = __float_as_uint(s_amax); }
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
+    const int n = i / H, kk = i % H;
+    const float v = w[i] * scale;                                   // exact (power of two)
+    if (pack_fwd) pack16_store(H, H, n, kk, v, pack_fwd);
+    if (pack_t) pack16_store(H, H, kk, n, v, pack_t);
+  }
 }
 // =====================================================================================================================
 // Fused node chain of one GCL (egnn/egnn_new.py:47-56) plus the first-layer projections that read its output:
@@ -1733,6 +1781,14 @@ int geoldm_tc_pack16(int H, const float* w, int n_out, int k, void* pack, void* 
 }
 int geoldm_tc_pack16_t(int H, const float* w_kn, int n_out, int k, void* pack, void* stream) {
   return tc_pack16_impl(H, w_kn, n_out, k, pack, stream, 1);
+}
+int geoldm_tc_pack16_pair(int H, const float* w, void* pack_fwd, void* pack_t, void* stream) {
+  GEOLDM_REQUIRE(H % 64 == 0 && H <= 256 && H > 0, "tc_pack16_pair: H=%d", H);
+  GEOLDM_REQUIRE(w != nullptr && (pack_fwd != nullptr || pack_t != nullptr), "tc_pack16_pair: null argument%s", "");
+  geoldm::pack16_pair_kernel<<<H * H / geoldm::PAIR_THREADS, geoldm::PAIR_THREADS, 0, (cudaStream_t)stream>>>(H, w, reinterpret_cast<uint8_t*>(pack_fwd),
+                                                                   reinterpret_cast<uint8_t*>(pack_t));
+  GEOLDM_CHECK_LAUNCH("pack16_pair_kernel");
+  return 0;
 }
 int geoldm_linear_tc_grad(int H, const float* dy, int ld, const void* w_pack, float* out, int m, void* amax_scratch,
                           void* stream) {

@@ -49,17 +49,28 @@ def _tc_ok(M: int, K: int, N: int) -> bool:
             and _lib.lib().geoldm_has_tcgen05() == 1)
 
 
-def _tc_linear(x, w_nk, bias, M, K, N):
-    """x [M,K] @ w_nk[N,K]^T (+ bias) through geoldm_tc_pack16 + geoldm_linear_tc (3xF16)."""
+def _tc_square(N, K):
+    return N == K and K in (64, 128, 192, 256)
+
+
+def _tc_linear(x, w_nk, bias, M, K, N, want_t=False):
+    """x [M,K] @ w_nk[N,K]^T (+ bias) through geoldm_tc_pack16 + geoldm_linear_tc (3xF16).  Square layers: both operand
+    images (this GEMM's and, want_t, the input-gradient GEMM's) come from ONE single-block pack launch; returns (out, pack_t)."""
     L = _lib.lib()
     hb = _tc_block(N)
     st = _stream(x)
     pack = torch.empty(L.geoldm_tc_pack16_bytes(hb, N, K), dtype=torch.uint8, device=x.device)
-    _lib.check(L.geoldm_tc_pack16(hb, _lib.ptr(w_nk), N, K, _lib.ptr(pack), st), "geoldm_tc_pack16(train)")
+    pack_t = None
+    if _tc_square(N, K):
+        if want_t:
+            pack_t = torch.empty_like(pack)
+        _lib.check(L.geoldm_tc_pack16_pair(K, _lib.ptr(w_nk), _lib.ptr(pack), _lib.ptr(pack_t), st), "geoldm_tc_pack16_pair")
+    else:
+        _lib.check(L.geoldm_tc_pack16(hb, _lib.ptr(w_nk), N, K, _lib.ptr(pack), st), "geoldm_tc_pack16(train)")
     out = torch.empty(M, N, device=x.device, dtype=torch.float32)
     _lib.check(L.geoldm_linear_tc(hb, 16, _lib.ptr(x), K, None, 0, 1.0, _lib.ptr(pack), N // hb, _lib.ptr(bias), None, 0,
                                   _lib.ptr(out), M, st), "geoldm_linear_tc(train)")
-    return out
+    return out, pack_t
 
 
 class _LinearFn(torch.autograd.Function):
@@ -71,8 +82,9 @@ class _LinearFn(torch.autograd.Function):
         x = x.contiguous()
         M, K = x.shape
         N = weight.shape[0]
+        ctx.pack_t = None
         if x.is_cuda and _tc_ok(M, K, N):
-            out = _tc_linear(x, weight.contiguous(), bias, M, K, N)
+            out, ctx.pack_t = _tc_linear(x, weight.contiguous(), bias, M, K, N, want_t=ctx.needs_input_grad[0])
             ctx.save_for_backward(x, weight)
             ctx.has_bias = bias is not None
             return out
@@ -99,10 +111,12 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             w = weight.contiguous()                       # [N][K] is already k-major for dX = dY W
             dx = torch.empty(M, K, device=x.device, dtype=torch.float32)
-            if N == K and K in (64, 128, 192, 256) and _tc_ok(M, N, K):
+            if _tc_square(N, K) and _tc_ok(M, N, K):
                 st = _stream(x)
-                pack = torch.empty(L.geoldm_tc_pack16_bytes(K, K, N), dtype=torch.uint8, device=x.device)
-                _lib.check(L.geoldm_tc_pack16_t(K, _lib.ptr(w), K, N, _lib.ptr(pack), st), "geoldm_tc_pack16_t(dX)")
+                pack = ctx.pack_t                          # packed together with the forward operand (same weight version)
+                if pack is None:
+                    pack = torch.empty(L.geoldm_tc_pack16_bytes(K, K, N), dtype=torch.uint8, device=x.device)
+                    _lib.check(L.geoldm_tc_pack16_pair(K, _lib.ptr(w), None, _lib.ptr(pack), st), "geoldm_tc_pack16_pair(dX)")
                 amax = torch.empty(1, dtype=torch.int32, device=x.device)
                 _lib.check(L.geoldm_linear_tc_grad(K, _lib.ptr(dy), N, _lib.ptr(pack), _lib.ptr(dx), M, _lib.ptr(amax), st),
                            "geoldm_linear_tc_grad(dX)")

@@ -222,6 +222,9 @@ int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2,
  * divides it out in the epilogue (both exact), so the result is as accurate as the forward GEMM regardless of the
  * magnitude of dy.  ld == H; amax_scratch: 4 bytes of device memory (overwritten). */
 int geoldm_tc_pack16_t(int H, const float* w_kn, int n_out, int k, void* pack, void* stream);
+/* both operand images of a SQUARE weight W [H][H] in one single-block launch: pack_fwd as geoldm_tc_pack16(H, W, H, H),
+ * pack_t as geoldm_tc_pack16_t(H, W, H, H) (either may be NULL); for weights that are re-packed every optimiser step */
+int geoldm_tc_pack16_pair(int H, const float* w, void* pack_fwd, void* pack_t, void* stream);
 int geoldm_linear_tc_grad(int H, const float* dy, int ld, const void* w_pack, float* out, int m, void* amax_scratch,
                           void* stream);
 /* descriptor / swizzle / pipeline self-test: out[row][0:H] = sum_k a[src_row[row]][k] * W[:, k] with a row stride
