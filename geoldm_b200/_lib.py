@@ -89,6 +89,9 @@ _SIGS = {
     "geoldm_train_edge_tail_fwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp]),
     "geoldm_train_edge_tail_bwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp,
                                              fp, fp, fp, fp, fp]),
+    "geoldm_adamw_ema_step": (C.c_int, [fp, fp, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_int, C.c_float, fp]),
+    "geoldm_optim_chunk": (C.c_int, []),
     "geoldm_train_coord2diff_fwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_float, fp, fp, fp]),
     "geoldm_train_coord2diff_bwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_float, fp, fp, fp, fp]),
     "geoldm_train_coord_step_fwd": (C.c_int, [C.c_int, fp, fp, fp, C.c_int, C.c_float, C.c_float, fp, fp]),

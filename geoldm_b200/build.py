@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgeoldm_b200.so")
-SOURCES = ["api.cu", "edge_simt.cu", "edge_tc.cu", "edge_tc16.cu", "linear.cu", "pack.cu", "sampler.cu", "stability.cu", "train.cu"]
+SOURCES = ["api.cu", "edge_simt.cu", "edge_tc.cu", "edge_tc16.cu", "linear.cu", "optim.cu", "pack.cu", "sampler.cu", "stability.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

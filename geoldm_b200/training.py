@@ -76,6 +76,74 @@ def get_optim(args, generative_model, capturable: bool = False):
     return torch.optim.AdamW(generative_model.parameters(), lr=args.lr, amsgrad=True, weight_decay=1e-12)
 
 
+class FusedAdamWEMA:
+    """`optim.step()` + `EMA.update_model_average` of a captured step as ONE launch of geoldm_adamw_ema_step over a device
+    table of (parameter, gradient, exp_avg, exp_avg_sq, max_exp_avg_sq, EMA copy, step) pointers.  The torch optimiser stays
+    the owner of the state: the kernel updates ITS tensors in place, so `optim.state_dict()` (the reference's checkpoint
+    format) keeps working, and a later eager `optim.step()` continues from the same moments.  Needs an AdamW built by
+    `get_optim(..., capturable=True)` whose state exists (one eager `optim.step()` has run) and float32 contiguous tensors.
+    Hyper-parameters are read when `step()` is called (during capture: baked into the graph, like the library's)."""
+
+    def __init__(self, optim, model, model_ema=None, ema: Optional[EMA] = None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        groups = optim.param_groups
+        if len(groups) != 1:
+            raise ValueError("FusedAdamWEMA: one parameter group expected (qm9/models.py:169-175)")
+        self.group = groups[0]
+        params = [p for p in self.group["params"] if p.requires_grad]
+        ema_of = {}
+        if model_ema is not None and ema is not None:
+            ema_of = {id(p): q for p, q in zip(model.parameters(), model_ema.parameters())}
+        self.ema_beta = float(ema.beta) if (ema is not None and model_ema is not None) else 1.0
+        self.amsgrad = bool(self.group.get("amsgrad", False))
+        dev = params[0].device
+        chunk = int(_lib.lib().geoldm_optim_chunk())
+        rows, cmap, self._keep = [], [], []
+        for p in params:
+            st = optim.state.get(p)
+            if not st or "exp_avg" not in st or not torch.is_tensor(st.get("step")) or not st["step"].is_cuda:
+                raise ValueError("FusedAdamWEMA: optimiser state missing (run one eager step of a capturable AdamW first)")
+            if p.grad is None:
+                raise ValueError("FusedAdamWEMA: every parameter needs a .grad tensor (FlatGradBuckets)")
+            tensors = [p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], st.get("max_exp_avg_sq") if self.amsgrad else None,
+                       ema_of.get(id(p)), st["step"]]
+            for t in tensors:
+                if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev):
+                    raise ValueError("FusedAdamWEMA: float32 contiguous tensors on one device expected")
+            self._keep.append(tensors)
+            ptrs = [0 if t is None else t.data_ptr() for t in tensors]
+            ti = len(rows)
+            rows.append(ptrs + [p.numel()])
+            cmap.extend((ti, off) for off in range(0, p.numel(), chunk))
+        # device table: 7 pointers + (int n, int pad) = 8 x 8 bytes per tensor
+        tab = torch.tensor([r[:7] + [r[7]] for r in rows], dtype=torch.int64)       # n in the low half of the last word
+        self.table = tab.to(dev)
+        self.chunk_map = torch.tensor(cmap, dtype=torch.int32).to(dev)
+        self.n_chunks = len(cmap)
+        self.step_count = self._keep[0][6].detach().clone().reshape(())             # shared update counter (device scalar)
+        self.grad_ptrs = [r[1] for r in rows]
+
+    def check_attached(self, optim):
+        """The gradient views must still be the tensors whose addresses are in the table."""
+        for tensors, ptr in zip(self._keep, self.grad_ptrs):
+            if tensors[1].data_ptr() != ptr:
+                raise RuntimeError("FusedAdamWEMA: a gradient tensor moved")
+
+    @torch.no_grad()
+    def step(self, grad_scale=None):
+        """One update.  grad_scale: optional device scalar multiplied into the gradients on the fly."""
+        g = self.group
+        self.step_count.add_(1.0)
+        stream = self._C.c_void_p(torch.cuda.current_stream(self.table.device).cuda_stream)
+        b1, b2 = g["betas"]
+        self._lib.check(self._lib.lib().geoldm_adamw_ema_step(
+            self._lib.ptr(self.table), self._lib.ptr(self.chunk_map), self.n_chunks, self._lib.ptr(self.step_count),
+            self._lib.ptr(grad_scale), float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+            int(self.amsgrad), float(self.ema_beta), stream), "geoldm_adamw_ema_step")
+
+
 class DeviceGradClip:
     """utils.py:29-66 (Queue + gradient_clipping) with the history on the DEVICE: the last 50 gradient norms in a ring
     buffer, threshold 1.5 mean + 2 std (population std, as np.std), clip coefficient max_norm / (norm + 1e-6) clamped to 1
@@ -268,8 +336,9 @@ class GraphedTrainStep:
 
     def __init__(self, args, model, optim, nodes_dist, x, h, node_mask, edge_mask, context, *, model_ema=None,
                  ema: Optional[EMA] = None, buckets: Optional[FlatGradBuckets] = None, clip: Optional[DeviceGradClip] = None,
-                 warmup: int = 3):
+                 warmup: int = 3, fused_optim: bool = True):
         dev = x.device
+        self.fused_optim = None
         self.args, self.model, self.optim, self.nodes_dist = args, model, optim, nodes_dist
         self.model_ema, self.ema = model_ema, ema
         self.buckets = buckets if buckets is not None else FlatGradBuckets(model)
@@ -289,6 +358,13 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # optimiser + EMA of the captured step as one multi-tensor launch (the warm-up above ran the library optimiser,
+        # which created its state); GEOLDM_FUSED_OPTIM=0 keeps the library's fused optimiser and the foreach EMA
+        self.fused_optim = None
+        import os
+        if fused_optim and os.environ.get("GEOLDM_FUSED_OPTIM", "1") != "0":
+            use_ema = self.ema is not None and self.model_ema is not None and getattr(self.args, "ema_decay", 0) > 0
+            self.fused_optim = FusedAdamWEMA(optim, model, self.model_ema if use_ema else None, self.ema if use_ema else None)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):
             self.nll, self.grad_norm = self._body()
@@ -301,9 +377,13 @@ class GraphedTrainStep:
         loss.backward()
         self.buckets.finish()
         grad_norm = self.clip.clip_(self.buckets.flat) if self.clip is not None else torch.zeros((), device=nll.device)
-        self.optim.step()
-        if self.ema is not None and self.model_ema is not None and getattr(self.args, "ema_decay", 0) > 0:
-            self.ema.update_model_average(self.model_ema, self.model)
+        if self.fused_optim is not None:
+            self.fused_optim.check_attached(self.optim)
+            self.fused_optim.step()
+        else:
+            self.optim.step()
+            if self.ema is not None and self.model_ema is not None and getattr(self.args, "ema_decay", 0) > 0:
+                self.ema.update_model_average(self.model_ema, self.model)
         return nll.detach(), grad_norm
 
     def close(self):
@@ -324,7 +404,10 @@ class GraphedTrainStep:
         if context is not None and self.context is not None:
             self.context.copy_(context, non_blocking=True)
         self.graph.replay()
-        for m in self.model.modules():                 # weights changed without python noticing: drop packed weight images
-            if hasattr(m, "_pack_key"):
-                m._pack_key = None
+        for net in (self.model, self.model_ema):       # weights changed without python noticing: drop packed weight images
+            if net is None:
+                continue
+            for m in net.modules():
+                if hasattr(m, "_pack_key"):
+                    m._pack_key = None
         return self.nll, self.grad_norm

@@ -260,6 +260,28 @@ int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float
                                double* dbw_scratch, /* [geoldm_train_bwd_blocks(n_edge) + 1] doubles, ZEROED once (the kernel leaves it zeroed), or
                                                      * NULL: dbw is accumulated with float atomics in arrival order (not reproducible) */
                                void* stream);
+/* AdamW(amsgrad) + EMA of the weights as ONE multi-tensor launch (qm9/models.py:169-175, utils.py:5-28,
+ * train_test.py:60-66).  table: one entry per parameter tensor (device array); chunk_map: n_chunks pairs {tensor index,
+ * first element} covering every tensor in pieces of geoldm_optim_chunk() elements (device array); step: device scalar, the
+ * update count INCLUDING this update (also stored to every entry's step); grad_scale: device scalar multiplied into the
+ * gradients (the clipping coefficient) or NULL; ema / vmax / step of an entry may be NULL.
+ *   p -= lr wd p;  m += (1 - b1)(g - m);  v = b2 v + (1 - b2) g^2;  vmax = max(vmax, v);
+ *   p -= lr / (1 - b1^step) * m / (sqrt(vmax) / sqrt(1 - b2^step) + eps);  ema = ema beta + (1 - beta) p */
+typedef struct geoldm_optim_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* vmax;
+  float* ema;
+  float* step;
+  int n;
+  int pad_;
+} geoldm_optim_tensor;
+int geoldm_adamw_ema_step(const geoldm_optim_tensor* table, const int* chunk_map, int n_chunks, const float* step,
+                          const float* grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          int amsgrad, float ema_beta, void* stream);
+int geoldm_optim_chunk(void);
 /* coord2diff and the coordinate update of EquivariantUpdate for the autograd path, forward and backward (one thread per
  * edge; egnn_new.py:249-255, 91-99):
  *   r[e] = |x_i - x_j|^2, u[e][3] = (x_i - x_j) / (sqrt(r + 1e-8) + norm_constant)   (u may be NULL: r only)
