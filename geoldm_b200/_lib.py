@@ -78,7 +78,7 @@ _SIGS = {
     "geoldm_tc_pack16": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
     "geoldm_tc_pack16_t": (C.c_int, [C.c_int, fp, C.c_int, C.c_int, fp, fp]),
     "geoldm_tc_pack16_pair": (C.c_int, [C.c_int, fp, fp, fp, fp]),
-    "geoldm_linear_tc_grad": (C.c_int, [C.c_int, fp, C.c_int, fp, fp, C.c_int, fp, fp]),
+    "geoldm_linear_tc_grad": (C.c_int, [C.c_int, fp, C.c_int, fp, fp, C.c_int, fp, C.c_int, fp]),
     "geoldm_linear_tc": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, C.c_int,
                                    fp, C.c_int, fp]),
     "geoldm_tc_selftest": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_int, fp, fp, fp]),
@@ -88,7 +88,7 @@ _SIGS = {
     "geoldm_train_edge_act_bwd": (C.c_int, [C.c_int, C.c_int, fp, C.c_int, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp]),
     "geoldm_train_edge_tail_fwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp]),
     "geoldm_train_edge_tail_bwd": (C.c_int, [C.c_int, C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, fp, C.c_float, fp, fp, fp,
-                                             fp, fp, fp, fp, fp]),
+                                             fp, fp, fp, fp, fp, fp]),
     "geoldm_adamw_ema_step": (C.c_int, [fp, fp, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                         C.c_int, C.c_float, fp]),
     "geoldm_optim_chunk": (C.c_int, []),

@@ -177,7 +177,7 @@ int launch_node_chain16(int H, const float* h, const float* agg, float agg_div, 
                         const void* pack2, const float* b2, const void* pack3, const float* b3, int n_pb, float* h_out,
                         float* pq_out, float* zero_buf, int m, cudaStream_t st);
 int launch_linear_tc16_grad(int H, const float* a_rows, int ld, const void* w_pack, float* out, int m, unsigned* amax_scratch,
-                            cudaStream_t st);
+                            int amax_ready, cudaStream_t st);
 int launch_tc16_selftest(int H, const float* pq, const int* edge_i, const int* tile_row, int n_tile, int n_rows,
                          const void* w_pack, float* out, cudaStream_t st);
 int launch_embed(int n_node, int H, int F, const float* h_in, const float* w, const float* b, float* h,

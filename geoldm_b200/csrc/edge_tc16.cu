@@ -1704,16 +1704,18 @@ int launch_linear_tc16(int H, const float* a1, int k1, const float* a2, int k2, 
 // input-gradient GEMM dX = dY W of a square Linear layer (dY is 1 / batch-size small: unscaled it leaves the normal fp16
 // range and the hi | lo split loses its low half).  amax_scratch: 4 bytes of device memory.
 int launch_linear_tc16_grad(int H, const float* a_rows, int ld, const void* w_pack, float* out, int m, unsigned* amax_scratch,
-                            cudaStream_t st) {
+                            int amax_ready, cudaStream_t st) {
   GEOLDM_REQUIRE(w_pack != nullptr && amax_scratch != nullptr, "linear_tc16_grad: w_pack / amax_scratch missing%s", "");
   GEOLDM_REQUIRE(ld % 4 == 0 && ld >= H && (reinterpret_cast<uintptr_t>(a_rows) & 15) == 0, "linear_tc16_grad: ld=%d", ld);
   if (m == 0) return 0;
-  cudaError_t e = cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned), st);
-  GEOLDM_REQUIRE(e == cudaSuccess, "linear_tc16_grad: memset: %s", cudaGetErrorString(e));
   GEOLDM_REQUIRE(ld == H, "linear_tc16_grad: the operand must be dense (ld=%d, H=%d)", ld, H);
-  const size_t tot = (size_t)m * H;
-  pack16_amax_kernel<<<(unsigned)((tot + 1023) / 1024 < 592 ? (tot + 1023) / 1024 : 592), 256, 0, st>>>(a_rows, tot, amax_scratch);
-  GEOLDM_CHECK_LAUNCH("pack16_amax_kernel(grad)");
+  if (!amax_ready) {
+    cudaError_t e = cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned), st);
+    GEOLDM_REQUIRE(e == cudaSuccess, "linear_tc16_grad: memset: %s", cudaGetErrorString(e));
+    const size_t tot = (size_t)m * H;
+    pack16_amax_kernel<<<(unsigned)((tot + 1023) / 1024 < 592 ? (tot + 1023) / 1024 : 592), 256, 0, st>>>(a_rows, tot, amax_scratch);
+    GEOLDM_CHECK_LAUNCH("pack16_amax_kernel(grad)");
+  }
   Args a{};
   a.n_tile = (m + TM - 1) / TM; a.n_rows = m; a.tile_row = nullptr; a.n_blocks = 1; a.n_slabs = H / BK;
   a.pq = a_rows; a.pq_ld = ld; a.edge_i = nullptr; a.w_pack = reinterpret_cast<const uint8_t*>(w_pack); a.out = out; a.ldo = H;
@@ -1791,8 +1793,9 @@ int geoldm_tc_pack16_pair(int H, const float* w, void* pack_fwd, void* pack_t, v
   return 0;
 }
 int geoldm_linear_tc_grad(int H, const float* dy, int ld, const void* w_pack, float* out, int m, void* amax_scratch,
-                          void* stream) {
-  return geoldm::launch_linear_tc16_grad(H, dy, ld, w_pack, out, m, reinterpret_cast<unsigned*>(amax_scratch), (cudaStream_t)stream);
+                          int amax_ready, void* stream) {
+  return geoldm::launch_linear_tc16_grad(H, dy, ld, w_pack, out, m, reinterpret_cast<unsigned*>(amax_scratch), amax_ready,
+                                         (cudaStream_t)stream);
 }
 static int tc_pack16_impl(int H, const float* w, int n_out, int k, void* pack, void* stream, int transposed) {
   GEOLDM_REQUIRE(H % 64 == 0 && H <= 256 && n_out % H == 0 && k % 64 == 0, "tc_pack16: H=%d n_out=%d k=%d", H, n_out, k);

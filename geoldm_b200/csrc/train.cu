@@ -342,11 +342,13 @@ __global__ void __launch_bounds__(32 * TRAIN_WARPS, GEOLDM_TRAIN_BWD_BLOCKS_PER_
                                      const float* __restrict__ w, const float* __restrict__ bw, int gate, int attention,
                                      const int* __restrict__ ei, float inv_div, const float* __restrict__ dagg,
                                      const float* __restrict__ dsc, float* __restrict__ dmpre, float* __restrict__ db2,
-                                     float* __restrict__ dw, float* __restrict__ dbw, double* __restrict__ bw_scratch) {
+                                     float* __restrict__ dw, float* __restrict__ dbw, double* __restrict__ bw_scratch,
+                                     unsigned* __restrict__ damax) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
   float acc_b[MAXG][4], acc_w[MAXG][4], bb[MAXG][4], ww[MAXG][4];
   double acc_bw = 0.0;      // attention-bias gradient: a cancelling sum over ALL edges, kept in double and summed in a fixed order
+  float omax = 0.f;         // max |dmpre| of this thread (-> damax: the scale of the input-gradient GEMM that consumes dmpre)
 #pragma unroll
   for (int g = 0; g < MAXG; ++g) {
 #pragma unroll
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WARPS, GEOLDM_TRAIN_BWD_BLOCKS_PER_
           if (w) { dm += ds * ww[g][t]; acc_w[g][t] += ds * m[g][t]; }
           o[t] = dm * dz[g][t];
           acc_b[g][t] += o[t];
+          omax = fmaxf(omax, fabsf(o[t]));
         }
         st4(dmpre + (size_t)e * H + c0, o);
       }
@@ -407,6 +410,19 @@ __global__ void __launch_bounds__(32 * TRAIN_WARPS, GEOLDM_TRAIN_BWD_BLOCKS_PER_
   __shared__ __align__(16) float red[TRAIN_WARPS][128 * MAXG];
   block_column_add(red, acc_b, H, db2);
   if (dw) block_column_add(red, acc_w, H, dw);
+  if (damax) {                                    // one atomic per block (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+    if (lane == 0) red[0][threadIdx.x >> 5] = omax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = red[0][0];
+#pragma unroll
+      for (int k = 1; k < TRAIN_WARPS; ++k) m = fmaxf(m, red[0][k]);
+      atomicMax(damax, __float_as_uint(m));
+    }
+    __syncthreads();
+  }
   if (dbw) {
     // block partial (double, fixed warp order) -> scratch[block]; the LAST block to finish adds all partials in a fixed
     // order (strided per thread, then a shared-memory tree: the whole block takes part, a single thread walking 592
@@ -573,7 +589,8 @@ int geoldm_train_edge_tail_fwd(int n_edge, int H, const float* mpre, const float
 }
 int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float* b2, const float* w, const float* bw,
                                int gate, int attention, const int* edge_i, float div, const float* dagg, const float* dsc,
-                               float* dmpre, float* db2, float* dw, float* dbw, double* dbw_scratch, void* stream) {
+                               float* dmpre, float* db2, float* dw, float* dbw, double* dbw_scratch, void* damax,
+                               void* stream) {
   using namespace geoldm;
   GEOLDM_REQUIRE(H > 0 && H <= 128 * MAXG && H % 4 == 0, "train_edge_tail: H=%d not a multiple of 4 in (0, %d]", H, 128 * MAXG);
   GEOLDM_REQUIRE(al16(mpre) && al16(b2) && al16(w) && al16(dagg) && al16(dmpre), "train_edge_tail_bwd: mpre / b2 / w / dagg / dmpre must be 16-byte aligned%s", "");
@@ -582,7 +599,7 @@ int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float
   edge_tail_bwd_kernel<<<train_grid_bwd(n_edge), 32 * TRAIN_WARPS, 0, (cudaStream_t)stream>>>(n_edge, H, mpre, b2, use_w ? w : nullptr, bw, gate, attention,
                                                                             edge_i, 1.0f / div, dagg, dsc, dmpre, db2,
                                                                             use_w ? dw : nullptr, (gate && attention) ? dbw : nullptr,
-                                                                            dbw_scratch);
+                                                                            dbw_scratch, reinterpret_cast<unsigned*>(damax));
   GEOLDM_CHECK_LAUNCH("edge_tail_bwd_kernel");
   return 0;
 }

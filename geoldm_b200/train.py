@@ -73,6 +73,55 @@ def _tc_linear(x, w_nk, bias, M, K, N, want_t=False):
     return out, pack_t
 
 
+# Direct gradient accumulation: a parameter registered here (training.FlatGradBuckets does it for every parameter whose
+# .grad is a view of a flat bucket) receives its weight / bias gradient straight from the GEMM kernel, which ACCUMULATES
+# into .grad (C += A^T B), instead of a zero-filled temporary that autograd then adds to .grad: one fill and one add launch
+# less per tensor.  `armed()` says whether .grad is currently valid as an accumulation target (between zero() and finish());
+# `hook(param)` is what the post-accumulate hook would have done (bucket bookkeeping, overlapped all-reduce).
+_DIRECT: dict = {}
+
+
+def register_direct_grad(param, armed, hook):
+    import weakref
+    _DIRECT[id(param)] = (weakref.ref(param), armed, hook)      # weak: the registry keeps no parameter alive
+
+
+def unregister_direct_grad(param):
+    _DIRECT.pop(id(param), None)
+
+
+def _direct_grad(t):
+    """The registered entry of tensor `t` if its gradient can be accumulated in place right now, else None."""
+    e = _DIRECT.get(id(t)) if t is not None else None
+    if e is None or e[0]() is not t or not e[1]():
+        return None
+    g = t.grad
+    if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous() or g.shape != t.shape:
+        return None
+    return e
+
+
+# max |dmpre| of the gradient tensor that _EdgeTailFn.backward just produced, offered to the input-gradient GEMM that
+# consumes it (the next node of the backward graph): one slot holding (tensor, amax).  The slot keeps the tensor alive, so
+# no other tensor can sit at its address while the offer stands; it is taken once or replaced by the next offer.
+_AMAX_OFFER = [None]
+
+
+def _offer_amax(t, amax):
+    _AMAX_OFFER[0] = (t, amax)
+
+
+def _take_amax(dy):
+    o = _AMAX_OFFER[0]
+    if o is None:
+        return None
+    _AMAX_OFFER[0] = None
+    t, amax = o
+    if t.data_ptr() == dy.data_ptr() and t.shape == dy.shape and t._version == 0 and dy.is_contiguous():
+        return amax
+    return None
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b on the geoldm_b200 GEMM kernels, x [M,K], W [N,K] (PyTorch layout): fp16-split tcgen05 for the forward
     and (square layers) the input gradient at edge-level row counts, fp32 FFMA otherwise and for dW."""
@@ -83,6 +132,8 @@ class _LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = weight.shape[0]
         ctx.pack_t = None
+        ctx.w_param = weight if id(weight) in _DIRECT else None
+        ctx.b_param = bias if (bias is not None and id(bias) in _DIRECT) else None
         if x.is_cuda and _tc_ok(M, K, N):
             out, ctx.pack_t = _tc_linear(x, weight.contiguous(), bias, M, K, N, want_t=ctx.needs_input_grad[0])
             ctx.save_for_backward(x, weight)
@@ -117,21 +168,39 @@ class _LinearFn(torch.autograd.Function):
                 if pack is None:
                     pack = torch.empty(L.geoldm_tc_pack16_bytes(K, K, N), dtype=torch.uint8, device=x.device)
                     _lib.check(L.geoldm_tc_pack16_pair(K, _lib.ptr(w), None, _lib.ptr(pack), st), "geoldm_tc_pack16_pair(dX)")
-                amax = torch.empty(1, dtype=torch.int32, device=x.device)
-                _lib.check(L.geoldm_linear_tc_grad(K, _lib.ptr(dy), N, _lib.ptr(pack), _lib.ptr(dx), M, _lib.ptr(amax), st),
-                           "geoldm_linear_tc_grad(dX)")
+                amax = _take_amax(dy)                       # max |dy| already found by the kernel that produced dy?
+                ready = amax is not None
+                if not ready:
+                    amax = torch.empty(1, dtype=torch.int32, device=x.device)
+                _lib.check(L.geoldm_linear_tc_grad(K, _lib.ptr(dy), N, _lib.ptr(pack), _lib.ptr(dx), M, _lib.ptr(amax),
+                                                   int(ready), st), "geoldm_linear_tc_grad(dX)")
             else:
                 _lib.check(L.geoldm_linear(_lib.ptr(dy), N, None, 0, 1.0, _lib.ptr(w), None, None, 0, _lib.ptr(dx), M, K, 0,
                                            _stream(x)), "geoldm_linear(dX)")
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             # dW and the bias gradient from ONE pass over dY (geoldm_gemm_tn_bias: the k0 == 0 blocks also add up the dY
-            # columns), both carved from one zero-filled allocation: no separate column-sum launch, one fill instead of two
-            buf = torch.zeros(N * K + (N if want_db else 0), device=x.device, dtype=torch.float32)
-            dw = buf[:N * K].view(N, K)
-            db = buf[N * K:] if want_db else None
-            _lib.check(L.geoldm_gemm_tn_bias(_lib.ptr(dy), N, _lib.ptr(x), K, _lib.ptr(dw), K, _lib.ptr(db), M, N, K,
+            # columns).  Targets: the parameters' own .grad when they are registered for direct accumulation (the kernel
+            # adds into its output), otherwise ONE zero-filled allocation for both, returned to autograd.
+            ew = _direct_grad(ctx.w_param)
+            eb = _direct_grad(ctx.b_param) if want_db else None
+            n_tmp = (0 if ew else N * K) + (N if (want_db and not eb) else 0)
+            buf = torch.zeros(n_tmp, device=x.device, dtype=torch.float32) if n_tmp else None
+            if ew:
+                dw_t = ew[0]().grad
+            else:
+                dw_t = dw = buf[:N * K].view(N, K)
+            db_t = None
+            if want_db:
+                if eb:
+                    db_t = eb[0]().grad
+                else:
+                    db_t = db = buf[(0 if ew else N * K):]
+            _lib.check(L.geoldm_gemm_tn_bias(_lib.ptr(dy), N, _lib.ptr(x), K, _lib.ptr(dw_t), K, _lib.ptr(db_t), M, N, K,
                                              _stream(x)), "geoldm_gemm_tn_bias(dW, db)")
+            for e in (ew, eb):
+                if e:
+                    e[2](e[0]())
         elif want_db:
             db = dy.sum(0)
         return dx, dw, db
@@ -226,6 +295,7 @@ class _EdgeTailFn(torch.autograd.Function):
         db2 = buf[:H]
         dw = None if w is None else buf[H:2 * H]
         dbw = None if bw is None else buf[2 * H:2 * H + 1]
+        amax = buf[2 * H + 1:2 * H + 2]                  # bit pattern of max |dmpre| (0.0f = 0u to start with)
         # scratch of the deterministic double-precision reduction of the attention-bias gradient: per-block partials + a
         # counter the kernel leaves at zero, so ONE zero-initialised buffer per (device, grid) serves every launch
         scratch = None
@@ -235,7 +305,8 @@ class _EdgeTailFn(torch.autograd.Function):
                                                          int(gate), int(attention), _lib.ptr(ei32), div,
                                                          _lib.ptr(dout) if gate else None, None if gate else _lib.ptr(dout),
                                                          _lib.ptr(dmpre), _lib.ptr(db2), _lib.ptr(dw), _lib.ptr(dbw),
-                                                         _lib.ptr(scratch), _stream(mpre)), "train_edge_tail_bwd")
+                                                         _lib.ptr(scratch), _lib.ptr(amax), _stream(mpre)), "train_edge_tail_bwd")
+        _offer_amax(dmpre, amax)
         if w is not None and not (attention or not gate):
             dw = None
         return dmpre, db2, dw, dbw, None, None, None, None, None

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import losses
+from . import losses, train
 
 
 class EMA:
@@ -228,7 +228,11 @@ class FlatGradBuckets:
     def __init__(self, model, group=None):
         self.group = group
         self.buckets = gradient_buckets(model)
-        self.flat, self._pending, self._works, self._hooks = [], [], [], []
+        self.flat, self._pending, self._works, self._hooks, self._direct = [], [], [], [], []
+        self._armed = False
+        import weakref
+        me = weakref.ref(self)
+        armed = lambda: bool(me() is not None and me()._armed)
         for bi, params in enumerate(self.buckets):
             n = sum(p.numel() for p in params)
             flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
@@ -236,7 +240,11 @@ class FlatGradBuckets:
             for p in params:
                 p.grad = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+                hook = self._make_hook(bi)
+                self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+                # the GEMM kernels may add a weight / bias gradient straight into the view (train._LinearFn.backward)
+                train.register_direct_grad(p, armed, lambda param, bi=bi: me() is not None and me()._make_hook(bi)(param))
+                self._direct.append(p)
             self.flat.append(flat)
             self._pending.append(0)
         self.nbytes = sum(f.numel() * f.element_size() for f in self.flat)
@@ -292,6 +300,9 @@ class FlatGradBuckets:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for p in self._direct:
+            train.unregister_direct_grad(p)
+        self._direct = []
 
 
 def train_step(args, model, optim, nodes_dist, x, h, node_mask, edge_mask, context, *, gradnorm_queue: Optional[Queue],

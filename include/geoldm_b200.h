@@ -220,13 +220,14 @@ int geoldm_linear_tc(int H, int terms, const float* a1, int k1, const float* a2,
  * [H out-features][H in-features] packed by geoldm_tc_pack16_t (the transposed operand).  dy is a GRADIENT (1 / batch-size
  * small): the kernel scales it by the power of two that puts max|dy| in [2^13, 2^14) before the fp16 hi | lo split and
  * divides it out in the epilogue (both exact), so the result is as accurate as the forward GEMM regardless of the
- * magnitude of dy.  ld == H; amax_scratch: 4 bytes of device memory (overwritten). */
+ * magnitude of dy.  ld == H; amax_scratch: 4 bytes of device memory, overwritten with the bit pattern of max|dy| unless
+ * amax_ready != 0: then it already holds it (written by the kernel that produced dy, geoldm_train_edge_tail_bwd). */
 int geoldm_tc_pack16_t(int H, const float* w_kn, int n_out, int k, void* pack, void* stream);
 /* both operand images of a SQUARE weight W [H][H] in one single-block launch: pack_fwd as geoldm_tc_pack16(H, W, H, H),
  * pack_t as geoldm_tc_pack16_t(H, W, H, H) (either may be NULL); for weights that are re-packed every optimiser step */
 int geoldm_tc_pack16_pair(int H, const float* w, void* pack_fwd, void* pack_t, void* stream);
 int geoldm_linear_tc_grad(int H, const float* dy, int ld, const void* w_pack, float* out, int m, void* amax_scratch,
-                          void* stream);
+                          int amax_ready, void* stream);
 /* descriptor / swizzle / pipeline self-test: out[row][0:H] = sum_k a[src_row[row]][k] * W[:, k] with a row stride
  * of 2H floats (the P|Q layout), rows split into tiles by tile_row like the edge kernels */
 int geoldm_tc_selftest(int H, int terms, const float* a, const int* src_row, const int* tile_row, int n_tile,
@@ -259,6 +260,8 @@ int geoldm_train_edge_tail_bwd(int n_edge, int H, const float* mpre, const float
                                float* dmpre, float* db2, float* dw, float* dbw,
                                double* dbw_scratch, /* [geoldm_train_bwd_blocks(n_edge) + 1] doubles, ZEROED once (the kernel leaves it zeroed), or
                                                      * NULL: dbw is accumulated with float atomics in arrival order (not reproducible) */
+                               void* damax,         /* 4 bytes, caller-zeroed, or NULL: bit pattern of max |dmpre| (what
+                                                     * geoldm_linear_tc_grad(..., amax_ready = 1) scales its operand by) */
                                void* stream);
 /* AdamW(amsgrad) + EMA of the weights as ONE multi-tensor launch (qm9/models.py:169-175, utils.py:5-28,
  * train_test.py:60-66).  table: one entry per parameter tensor (device array); chunk_map: n_chunks pairs {tensor index,
