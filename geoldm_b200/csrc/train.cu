@@ -650,7 +650,10 @@ extern "C" int geoldm_gemm_tn_bias(const float* a, int lda, const float* b, int 
   GEOLDM_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "gemm_tn: lda=%d ldb=%d must be multiples of 4", lda, ldb);
   if (m == 0 || n == 0 || k == 0) return 0;
   const int tiles = ((n + TN_BN - 1) / TN_BN) * ((k + TN_BK - 1) / TN_BK);
-  int splits = (3 * 148) / tiles;                              // one resident wave: 3 CTAs of 66 registers x 256 threads per SM
+#ifndef GEOLDM_TN_CTAS_PER_SM
+#define GEOLDM_TN_CTAS_PER_SM 3
+#endif
+  int splits = (GEOLDM_TN_CTAS_PER_SM * 148) / tiles;          // one resident wave: 3 CTAs of 66 registers x 256 threads per SM
   const int max_splits = (m + 4 * TN_BM - 1) / (4 * TN_BM);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
