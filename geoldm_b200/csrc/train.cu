@@ -6,7 +6,12 @@
 
 namespace geoldm {
 namespace {
-constexpr int TN_BN = 64, TN_BK = 64, TN_BM = 16, TN_T = 256;
+#ifndef GEOLDM_TN_RT
+#define GEOLDM_TN_RT 8
+#endif
+// TN_RT x 4 outputs per thread: 4 -> 256 threads, 8 -> 128 threads per 64 x 64 tile (fewer shared-memory operand reads per FMA)
+constexpr int TN_BN = 64, TN_BK = 64, TN_BM = 16, TN_RT = GEOLDM_TN_RT, TN_T = 16 * (TN_BN / TN_RT);
+constexpr int TN_LR = TN_T / 16, TN_LPT = TN_BM / TN_LR;      // loader rows per pass, passes per slab
 
 __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b,
                                                       int ldb, float* __restrict__ c, int ldc, int m, int n, int k,
@@ -17,38 +22,44 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
   const int n0 = blockIdx.y * TN_BN, k0 = blockIdx.x * TN_BK;
   const int m_begin = blockIdx.z * m_per_split;
   const int m_end = min(m, m_begin + m_per_split);
-  const int tr = t >> 4, tc = t & 15;            // 16 x 16 threads, 4 x 4 outputs each
+  const int tr = t >> 4, tc = t & 15;            // (64 / TN_RT) x 16 threads, TN_RT x 4 outputs each
   // loaders: thread -> (row = t / 16, 4 consecutive columns)
   const int lr = t >> 4, lc = (t & 15) * 4;
   // accumulators as packed fp32 pairs along the output columns: fma.rn.f32x2 performs two IEEE FMAs per issue slot (the
   // plain three-register FFMA issues every second cycle per scheduler on sm_100), same products and summation order
-  f32x2 acc2[4][2];
+  f32x2 acc2[TN_RT][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = pk2(0.f, 0.f);
+  for (int i = 0; i < TN_RT; ++i) acc2[i][0] = acc2[i][1] = pk2(0.f, 0.f);
 
   // global -> registers (issued before the FMAs of the current slab) -> shared (after them): the L2 latency of the next
   // 16-row slab is hidden behind 256 FMAs per thread instead of being exposed at every slab
-  float4 va, vb;
+  float4 va[TN_LPT], vb[TN_LPT];
   // bias gradient (colsum[n] += sum_m A[m][n], optional): the k0 == 0 blocks add up the A values they stage anyway, one
-  // float4 per thread and slab, and combine the 16 row phases through shared memory at the end
+  // float4 per thread and slab, and combine the row phases through shared memory at the end
   const bool do_colsum = colsum != nullptr && blockIdx.x == 0;
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   auto g_load = [&](int mrow) {
-    va = make_float4(0.f, 0.f, 0.f, 0.f); vb = va;
-    const int mm = mrow + lr;
-    if (mm < m_end) {
-      const float* pa = a + (size_t)mm * lda + n0 + lc;
-      const float* pb = b + (size_t)mm * ldb + k0 + lc;
-      if (n0 + lc + 3 < n) va = __ldg(reinterpret_cast<const float4*>(pa));
-      else { float tmp[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (n0 + lc + e < n) tmp[e] = pa[e]; va = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]); }
-      if (k0 + lc + 3 < k) vb = __ldg(reinterpret_cast<const float4*>(pb));
-      else { float tmp[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (k0 + lc + e < k) tmp[e] = pb[e]; vb = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]); }
+#pragma unroll
+    for (int q = 0; q < TN_LPT; ++q) {
+      va[q] = make_float4(0.f, 0.f, 0.f, 0.f); vb[q] = va[q];
+      const int mm = mrow + lr + q * TN_LR;
+      if (mm < m_end) {
+        const float* pa = a + (size_t)mm * lda + n0 + lc;
+        const float* pb = b + (size_t)mm * ldb + k0 + lc;
+        if (n0 + lc + 3 < n) va[q] = __ldg(reinterpret_cast<const float4*>(pa));
+        else { float tmp[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (n0 + lc + e < n) tmp[e] = pa[e]; va[q] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]); }
+        if (k0 + lc + 3 < k) vb[q] = __ldg(reinterpret_cast<const float4*>(pb));
+        else { float tmp[4] = {0.f, 0.f, 0.f, 0.f}; for (int e = 0; e < 4; ++e) if (k0 + lc + e < k) tmp[e] = pb[e]; vb[q] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]); }
+      }
     }
   };
   auto s_store = [&](int buf) {
-    cs.x += va.x; cs.y += va.y; cs.z += va.z; cs.w += va.w;
-    *reinterpret_cast<float4*>(&As[buf][lr][lc]) = va;
-    *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = vb;
+#pragma unroll
+    for (int q = 0; q < TN_LPT; ++q) {
+      cs.x += va[q].x; cs.y += va[q].y; cs.z += va[q].z; cs.w += va[q].w;
+      *reinterpret_cast<float4*>(&As[buf][lr + q * TN_LR][lc]) = va[q];
+      *reinterpret_cast<float4*>(&Bs[buf][lr + q * TN_LR][lc]) = vb[q];
+    }
   };
 
   int buf = 0;
@@ -59,12 +70,16 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
     if (more) g_load(mrow + TN_BM);
 #pragma unroll
     for (int mm = 0; mm < TN_BM; ++mm) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[buf][mm][tr * 4]);
+      float ar[TN_RT];
+#pragma unroll
+      for (int h = 0; h < TN_RT / 4; ++h) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[buf][mm][tr * TN_RT + 4 * h]);
+        ar[4 * h] = av.x; ar[4 * h + 1] = av.y; ar[4 * h + 2] = av.z; ar[4 * h + 3] = av.w;
+      }
       const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][mm][tc * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w};
       const f32x2 b01 = pk2(bv.x, bv.y), b23 = pk2(bv.z, bv.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TN_RT; ++i) {
         const f32x2 aa = pk2(ar[i], ar[i]);
         acc2[i][0] = fma2(aa, b01, acc2[i][0]);
         acc2[i][1] = fma2(aa, b23, acc2[i][1]);
@@ -75,12 +90,12 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
     buf ^= 1;
   }
   const bool vec_out = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15u) == 0;
-  float acc[4][4];
+  float acc[TN_RT][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { upk2(acc2[i][0], acc[i][0], acc[i][1]); upk2(acc2[i][1], acc[i][2], acc[i][3]); }
+  for (int i = 0; i < TN_RT; ++i) { upk2(acc2[i][0], acc[i][0], acc[i][1]); upk2(acc2[i][1], acc[i][2], acc[i][3]); }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int nn = n0 + tr * 4 + i;
+  for (int i = 0; i < TN_RT; ++i) {
+    const int nn = n0 + tr * TN_RT + i;
     if (nn >= n) continue;
     const int kk0 = k0 + tc * 4;
     if (vec_out && kk0 + 3 < k) {     // one 16-byte vector reduction instead of four scalar ones (L2 reduction operations / 4)
@@ -101,7 +116,7 @@ __global__ void __launch_bounds__(TN_T) gemm_tn_kernel(const float* __restrict__
     if (t < TN_BN && n0 + t < n) {
       float v = 0.f;
 #pragma unroll
-      for (int rr = 0; rr < TN_BM; ++rr) v += As[0][rr][t];
+      for (int rr = 0; rr < TN_LR; ++rr) v += As[0][rr][t];
       atomicAdd(colsum + n0 + t, v);
     }
   }
@@ -653,7 +668,7 @@ extern "C" int geoldm_gemm_tn_bias(const float* a, int lda, const float* b, int 
 #ifndef GEOLDM_TN_CTAS_PER_SM
 #define GEOLDM_TN_CTAS_PER_SM 3
 #endif
-  int splits = (GEOLDM_TN_CTAS_PER_SM * 148) / tiles;          // one resident wave: 3 CTAs of 66 registers x 256 threads per SM
+  int splits = (GEOLDM_TN_CTAS_PER_SM * (256 / TN_T) * 148) / tiles;          // one resident wave: 3 CTAs of 66 registers x 256 threads per SM
   const int max_splits = (m + 4 * TN_BM - 1) / (4 * TN_BM);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
