@@ -391,7 +391,11 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
     info = {"atom_decoder": list(range(5)), "n_nodes": hist, "max_n_nodes": 29}
     torch.manual_seed(0)                                        # identical init on every rank
     model, nodes_dist, _ = get_latent_diffusion(args, dev, info, None)
-    nodes = histogram_nodes(hist, world * bs, seed=5)[rank * bs:(rank + 1) * bs]
+    # the global batch of world x 64 molecules, dealt over the ranks with equal molecule counts and balanced edge counts
+    # (packing.balance_shards_equal: the step is as slow as its slowest rank); one rank: the batch as drawn
+    from geoldm_b200.packing import balance_shards_equal
+    all_nodes = np.asarray(histogram_nodes(hist, world * bs, seed=5))
+    nodes = all_nodes[balance_shards_equal(all_nodes, world)[rank]] if world > 1 else all_nodes
     gen = torch.Generator().manual_seed(11 + rank)
     nm, em = build_masks(torch.as_tensor(nodes), 29, dev)
     x = losses.remove_mean_with_mask(torch.randn(bs, 29, 3, generator=gen).to(dev) * nm, nm)
@@ -427,8 +431,8 @@ def bench_train(mode, dev, rank, world, dist, steps=6):
     step.close()                                               # the graph holds NCCL work: release it before the process group goes
     nll = torch.tensor(last_nll)
     return {"workload": "BASELINE.json configs[4]: conditional QM9 GeoLDM training step, nf=192 n_layers=9, 64 molecules "
-                        "per GPU, trainable first stage, AdamW + EMA, gradient all-reduce over NCCL; the step is one captured CUDA graph "
-                        "(training.GraphedTrainStep)",
+                        "per GPU (the global batch dealt over the ranks by edge count, equal molecule counts), trainable first stage, "
+                        "AdamW + EMA, gradient all-reduce over NCCL; the step is one captured CUDA graph (training.GraphedTrainStep)",
             "molecules_per_gpu": bs, "n_gpus": world, "ms_per_step": ms, "molecules_per_s": world * bs / (ms * 1e-3),
             "allreduce_bytes_per_step": nbytes if world > 1 else 0, "last_nll": float(nll), "finite": bool(torch.isfinite(nll))}
 

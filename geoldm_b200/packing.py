@@ -152,6 +152,23 @@ def pack_from_masks(node_mask: torch.Tensor, edge_mask: Optional[torch.Tensor] =
     return pack_molecules(n_arr, node_mask.device, n_max=n, positions=positions)
 
 
+def balance_shards_equal(n_nodes: Sequence[int], world_size: int):
+    """Split of a TRAINING batch over ranks: every rank gets the same number of molecules (the loss is a per-rank mean that
+    is averaged over ranks, like the equal chunks of the reference's DataParallel scatter, main_qm9.py:234-239) and about
+    the same number of edges (a step takes as long as its slowest rank): molecules sorted by edge count are dealt
+    boustrophedon (ranks 0..W-1, W-1..0, ...).  len(n_nodes) must be a multiple of world_size.  Returns per-rank index
+    arrays into n_nodes, each sorted ascending; identical on every rank."""
+    n_arr = np.asarray(n_nodes, dtype=np.int64)
+    if len(n_arr) % world_size != 0:
+        raise ValueError(f"balance_shards_equal: {len(n_arr)} molecules do not split evenly over {world_size} ranks")
+    cost = n_arr * (n_arr - 1) + n_arr
+    order = np.argsort(-cost, kind="stable")
+    k = np.arange(len(order))
+    rnd, pos = k // world_size, k % world_size
+    rank = np.where(rnd % 2 == 0, pos, world_size - 1 - pos)
+    return [np.sort(order[rank == r]).astype(np.int64) for r in range(world_size)]
+
+
 def balance_shards(n_nodes: Sequence[int], world_size: int):
     """Greedy longest-processing-time split of molecules over ranks by edge count n(n-1).
     Returns a list (per rank) of index arrays into n_nodes, each sorted ascending."""

@@ -108,6 +108,21 @@ def test_balance_shards():
     assert max(loads) / min(loads) < 1.005
 
 
+def test_balance_shards_equal_counts():
+    """Training batches: equal molecule counts per rank (per-rank mean losses are averaged), edge counts within 2 %."""
+    from geoldm_b200.packing import balance_shards_equal
+    rng = np.random.default_rng(1)
+    for world in (2, 4, 8):
+        n = rng.integers(3, 30, size=64 * world)
+        shards = balance_shards_equal(n, world)
+        assert all(len(s) == 64 for s in shards) and all(np.all(np.diff(s) > 0) for s in shards)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(64 * world))
+        loads = [int((n[s] * (n[s] - 1)).sum()) for s in shards]
+        assert max(loads) / min(loads) < 1.02, (world, loads)
+    with pytest.raises(ValueError):
+        balance_shards_equal(np.arange(3, 13), 4)
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for philox4x32-10."""
     from tests.philox_ref import philox4x32_10
