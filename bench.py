@@ -46,6 +46,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+# environment sets NCCL_DEBUG): file descriptor 1 is pointed at stderr for the whole run and the result line goes to the
+# saved descriptor.
+_RESULT_FD = None
+
+
+def claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -242,7 +265,7 @@ def run_reference(args):
             "edge_msgs_per_s": 18 * edges / sec,
             "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -450,6 +473,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs.latency64 / geom32 / train measurements")
     ap.add_argument("--mols-per-gpu", type=int, default=MOLS_PER_GPU)
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -662,7 +686,7 @@ def main():
                              "flops": "E (2 H^2 + 2 H): second edge layer + head dot; 3 fp16 MMAs are issued per product",
                              "peak_source": peak_src},
                 "cpu_baseline": cpu, "configs": extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
