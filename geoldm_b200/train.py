@@ -1,14 +1,16 @@
 """Training-side (autograd) path of the EGNN wrappers — SURVEY §8 configs 2 and 5.
 
-Correctness-first companion of the fused inference kernels: the network is evaluated on the same ragged packing, every
-``nn.Linear`` with GEMM-sized dimensions runs on this repo's fp32 CUDA kernels in all three directions
-(forward ``geoldm_linear``, input gradient ``geoldm_linear`` with the untransposed weight, weight gradient
-``geoldm_gemm_tn``) through ``torch.autograd.Function``, and the element-wise stages of both edge MLPs (gather + first
-SiLU; bias + second SiLU + attention gate + segment sum / coordinate head) run as fused forward/backward CUDA kernels
-(``geoldm_train_edge_act_*``, ``geoldm_train_edge_tail_*``, csrc/train.cu).  The remaining node-level element-wise ops, the
-1-3-wide heads and ``coord2diff`` are library ops recorded by autograd.  It shares the ``nn.Parameter`` objects of the inference modules, so optimisers, EMA and
-``DistributedDataParallel`` (NCCL gradient all-reduce) work unchanged.  A fused recompute-in-kernel backward on the
-tensor cores is round-2 work.
+Companion of the fused inference kernels: the network is evaluated on the same ragged packing.  Every ``nn.Linear`` with
+GEMM-sized dimensions runs on this repo's kernels in all three directions through ``torch.autograd.Function``: edge-level
+forward and input-gradient GEMMs on the tcgen05 fp16-split kernel (``geoldm_linear_tc`` / ``geoldm_linear_tc_grad``, the
+gradient operand pre-scaled by a power of two), node-level GEMMs on the fp32 kernel (``geoldm_linear``), weight and bias
+gradients on ``geoldm_gemm_tn_bias``, accumulated straight into ``.grad`` where the parameter is registered for it
+(``register_direct_grad``, training.FlatGradBuckets).  The element-wise stages of both edge MLPs (gather + first SiLU; bias +
+second SiLU + attention gate + segment sum / coordinate head), ``coord2diff`` and the coordinate update run as fused
+forward/backward CUDA kernels (``geoldm_train_edge_act_*``, ``geoldm_train_edge_tail_*``, ``geoldm_train_coord2diff_*``,
+``geoldm_train_coord_step_*``, csrc/train.cu).  The remaining node-level element-wise ops and the 1-3-wide heads are library
+ops recorded by autograd.  It shares the ``nn.Parameter`` objects of the inference modules, so optimisers, EMA and the NCCL
+gradient all-reduce work unchanged.  A recompute-in-tile backward on the tensor cores is not built.
 
 Reference: egnn/egnn_new.py:30-65,86-105,134-147,184-197; egnn/models.py:49-113,335-381.
 """
