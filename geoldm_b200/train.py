@@ -75,6 +75,73 @@ def _tc_linear(x, w_nk, bias, M, K, N, want_t=False):
     return out, pack_t
 
 
+# Zero-filled temporaries of one optimisation step from ONE arena that is cleared with a single fill at the top of the step
+# (training.FlatGradBuckets.zero() / finish() bracket the step), instead of one fill launch per temporary (~230 per step:
+# scatter targets of the fused kernels, weight-gradient buffers).  The first bracketed step only measures; the arena is
+# allocated after it (outside any graph capture) and serves the following steps, whose allocation sequence is the same for
+# the same batch signature; anything that does not fit falls back to torch.zeros.  Tensors are handed out as independent
+# aliases of the arena's storage (no view relationship, own version counters).  Everything taken from the arena is dead
+# when the step ends: gradients reach the parameters through the flat buckets, never by handing one of these tensors over
+# (which is why the arena is tied to FlatGradBuckets: there .grad always exists, so autograd adds instead of keeping).
+class _ZeroArena:
+    def __init__(self):
+        self.buf, self.off, self.need, self.active, self.measuring = None, 0, 0, False, False
+        self._retired = []          # outgrown buffers stay allocated: a captured graph may still write to them on replay
+
+    @staticmethod
+    def _al(n):
+        return (n + 63) // 64 * 64                      # 256-byte pieces: vector accesses stay aligned
+
+    def begin(self):
+        if self.active or self.measuring:               # nested / interleaved steps: stand aside
+            self.active = self.measuring = False
+            return
+        self.off, self.need = 0, 0
+        if self.buf is not None:
+            self.buf.zero_()
+            self.active = True
+        else:
+            self.measuring = True
+
+    def end(self, device):
+        if self.measuring and self.need > 0 and not torch.cuda.is_current_stream_capturing():
+            self.buf = torch.empty(self.need, dtype=torch.float32, device=device)
+        elif self.active and self.need > self.buf.numel() and not torch.cuda.is_current_stream_capturing():
+            self._retired.append(self.buf)
+            self.buf = torch.empty(self.need, dtype=torch.float32, device=device)      # a larger batch came along
+        self.active = self.measuring = False
+
+    def zeros(self, n, device):
+        a = self._al(n)
+        self.need += a
+        if self.active and self.buf.device == device and self.off + a <= self.buf.numel():
+            t = torch.empty(0, dtype=torch.float32, device=device).set_(self.buf.untyped_storage(), self.off, (n,), (1,))
+            self.off += a
+            return t
+        return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+_ARENAS: dict = {}
+
+
+def arena_begin(device):
+    if device.type == "cuda":
+        _ARENAS.setdefault(device.index, _ZeroArena()).begin()
+
+
+def arena_end(device):
+    if device.type == "cuda" and device.index in _ARENAS:
+        _ARENAS[device.index].end(device)
+
+
+def _zeros(n, device):
+    """n zero-filled float32 values: from the step's arena when one is open on this device, else a fresh tensor."""
+    a = _ARENAS.get(device.index) if device.type == "cuda" else None
+    if a is None or not (a.active or a.measuring):
+        return torch.zeros(n, dtype=torch.float32, device=device)
+    return a.zeros(n, device)
+
+
 # Direct gradient accumulation: a parameter registered here (training.FlatGradBuckets does it for every parameter whose
 # .grad is a view of a flat bucket) receives its weight / bias gradient straight from the GEMM kernel, which ACCUMULATES
 # into .grad (C += A^T B), instead of a zero-filled temporary that autograd then adds to .grad: one fill and one add launch
@@ -187,7 +254,7 @@ class _LinearFn(torch.autograd.Function):
             ew = _direct_grad(ctx.w_param)
             eb = _direct_grad(ctx.b_param) if want_db else None
             n_tmp = (0 if ew else N * K) + (N if (want_db and not eb) else 0)
-            buf = torch.zeros(n_tmp, device=x.device, dtype=torch.float32) if n_tmp else None
+            buf = _zeros(n_tmp, x.device) if n_tmp else None
             if ew:
                 dw_t = ew[0]().grad
             else:
@@ -254,7 +321,7 @@ class _EdgeActFn(torch.autograd.Function):
         pq, r, d0, w_rd, ei32, ej32 = ctx.saved_tensors
         E, H = ei32.numel(), w_rd.shape[1]
         da = da.contiguous()
-        buf = torch.zeros(pq.numel() + w_rd.numel(), device=pq.device, dtype=torch.float32)   # one fill for both
+        buf = _zeros(pq.numel() + w_rd.numel(), pq.device)                                    # one fill for both
         dpq = buf[:pq.numel()].view_as(pq)
         dw = buf[pq.numel():].view_as(w_rd)
         dr = torch.empty(E, device=pq.device, dtype=torch.float32)
@@ -276,7 +343,7 @@ class _EdgeTailFn(torch.autograd.Function):
         E, H = mpre.shape
         w = None if w is None else w.contiguous()
         dev = mpre.device
-        agg = torch.zeros(n_node, H, device=dev, dtype=torch.float32) if gate else None
+        agg = _zeros(n_node * H, dev).view(n_node, H) if gate else None
         sc = None if gate else torch.empty(E, 1, device=dev, dtype=torch.float32)
         _lib.check(_lib.lib().geoldm_train_edge_tail_fwd(E, H, _lib.ptr(mpre), _lib.ptr(b2), _lib.ptr(w), _lib.ptr(bw),
                                                          int(gate), int(attention), _lib.ptr(ei32), float(div),
@@ -293,7 +360,7 @@ class _EdgeTailFn(torch.autograd.Function):
         dout = dout.contiguous()
         dmpre = torch.empty_like(mpre)
         # db2 | dw | dbw carved from one zero-filled allocation (H is a multiple of 4: the vector pieces stay 16-byte aligned)
-        buf = torch.zeros(2 * H + 4, device=mpre.device, dtype=torch.float32)
+        buf = _zeros(2 * H + 4, mpre.device)
         db2 = buf[:H]
         dw = None if w is None else buf[H:2 * H]
         dbw = None if bw is None else buf[2 * H:2 * H + 1]
@@ -377,7 +444,7 @@ class _Coord2DiffFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gr, gu):
         xc, ei32, ej32 = ctx.saved_tensors
-        gx = torch.zeros_like(xc)
+        gx = _zeros(xc.numel(), xc.device).view_as(xc)
         gr = None if gr is None else gr.contiguous()
         gu = None if gu is None else gu.contiguous()
         _lib.check(_lib.lib().geoldm_train_coord2diff_bwd(ei32.numel(), _lib.ptr(xc), _lib.ptr(ei32), _lib.ptr(ej32), ctx.c,
@@ -393,7 +460,7 @@ class _CoordStepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, sc, ei32, n_node, use_tanh, coords_range, div):
         u, sc = u.contiguous(), sc.contiguous()
-        step = torch.zeros(n_node, 3, device=u.device, dtype=torch.float32)
+        step = _zeros(n_node * 3, u.device).view(n_node, 3)
         ctx.cfg = (int(bool(use_tanh)), float(coords_range), float(div))
         _lib.check(_lib.lib().geoldm_train_coord_step_fwd(ei32.numel(), _lib.ptr(u), _lib.ptr(sc), _lib.ptr(ei32), *ctx.cfg,
                                                           _lib.ptr(step), _stream(u)), "train_coord_step_fwd")
