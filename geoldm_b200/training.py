@@ -277,13 +277,15 @@ class FlatGradBuckets:
             self._pending[bi] = len(params)
         self._works = []
         self._armed = True
-        train.arena_begin(self.flat[0].device)        # zero-filled temporaries of this step: one arena, one fill
+        if self.flat:
+            train.arena_begin(self.flat[0].device)    # zero-filled temporaries of this step: one arena, one fill
 
     def finish(self) -> int:
         """After backward: launch what the hooks could not (parameters that received no gradient on this rank keep
         their zeros; every rank issues the same collectives), wait, average.  Returns the bytes all-reduced."""
         self._armed = False
-        train.arena_end(self.flat[0].device)
+        if self.flat:
+            train.arena_end(self.flat[0].device)
         if not self._distributed():
             return 0
         for bi, flat in enumerate(self.flat):
