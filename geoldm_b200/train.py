@@ -104,9 +104,10 @@ class _ZeroArena:
             self.measuring = True
 
     def end(self, device):
-        if self.measuring and self.need > 0 and not torch.cuda.is_current_stream_capturing():
+        capturing = device.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if self.measuring and self.need > 0 and not capturing:
             self.buf = torch.empty(self.need, dtype=torch.float32, device=device)
-        elif self.active and self.need > self.buf.numel() and not torch.cuda.is_current_stream_capturing():
+        elif self.active and self.need > self.buf.numel() and not capturing:
             self._retired.append(self.buf)
             self.buf = torch.empty(self.need, dtype=torch.float32, device=device)      # a larger batch came along
         self.active = self.measuring = False
